@@ -54,6 +54,8 @@ def rnd64(seed: int, stream: int, a, b=0) -> np.ndarray:
 class Genome:
     names: List[str]
     seqs: List[np.ndarray]  # uint8 ASCII, upper case ACGTN
+    repeat_copies: List[Tuple[int, int, int, int, int]] = dataclasses.field(default_factory=list)  # (family, copy, contig, offset, len)
+    motif_sites: List[Tuple[int, int, int]] = dataclasses.field(default_factory=list)              # (motif, contig, offset)
 
     @property
     def lengths(self) -> List[int]:
@@ -89,6 +91,7 @@ def make_genome(
         r = rnd64(seed, 1, ci, np.arange(length, dtype=U64))
         seqs.append(BASES[(r >> U64(33)).astype(np.int64) & 3].copy())
     total = [s.size for s in seqs]
+    rep_meta, mot_meta = [], []
 
     def place(stream, key, seg_len):
         r = int(rnd64(seed, stream, key))
@@ -107,14 +110,16 @@ def make_genome(
                 p = r % fam_len
                 seg[p] = BASES[(int(_CODE[seg[p]]) + 1 + ((r >> 40) % 3)) & 3]
             seqs[cj][o2:o2 + fam_len] = seg
+            rep_meta.append((fam_id, c, cj, o2, fam_len))
     for mi, (motif, times) in enumerate(motifs):
         mot = np.frombuffer(motif, dtype=np.uint8)
         for t in range(times):
             cj, o2 = place(5, mi * 100000 + t, mot.size)
             seqs[cj][o2:o2 + mot.size] = mot
+            mot_meta.append((mi, cj, o2))
     for ci, start, length in n_runs:
         seqs[ci][start:start + length] = ord("N")
-    return Genome([n for n, _ in contigs], seqs)
+    return Genome([n for n, _ in contigs], seqs, rep_meta, mot_meta)
 
 
 def write_fasta(genome: Genome, path: str, width: int = 60) -> None:
@@ -264,6 +269,9 @@ def simulate_reads(
     id_width: int = 9,
     lower_rate: float = 0.0,
     n_rate: float = 0.0,
+    forced_starts: Optional[np.ndarray] = None,
+    forced_rev: Optional[np.ndarray] = None,
+    qual_alphabet: Optional[bytes] = None,
 ) -> np.ndarray:
     """FASTQ text (uint8 array) of `n_reads` fixed-length records.
 
@@ -272,6 +280,9 @@ def simulate_reads(
     the first `lowq_chars` is below '8' with probability `lowq_prob` (that is the character the
     reference gates the neighbour search of k-mer i on: src/qv.cc:836,943), all others are >= '8'.
     lower_rate / n_rate: per-base probability of lower-casing / replacing by 'N' (adversarial sets).
+    forced_starts / forced_rev: per-read global 0-based start and strand instead of the random ones
+    (targeted reads: put a planted motif on bases 16..31 of a k-mer).
+    qual_alphabet: when given, every quality character is drawn uniformly from it instead.
     """
     lens = np.array(genome.lengths, dtype=np.int64)
     starts = genome.starts
@@ -282,10 +293,15 @@ def simulate_reads(
     r0 = rnd64(seed, 30, rid)
     s = (r0 % U64(total - L + 1)).astype(np.int64)
     ci = np.searchsorted(starts, s, side="right") - 1
+    if forced_starts is not None:
+        s = np.asarray(forced_starts, dtype=np.int64)
+        ci = np.searchsorted(starts, s, side="right") - 1
     s = np.minimum(s, starts[ci] + lens[ci] - L)
     r1 = rnd64(seed, 31, rid)
     hap = ((r1 >> U64(7)) & U64(1)).astype(bool)
     rev = ((r1 >> U64(9)) & U64(1)).astype(bool)
+    if forced_rev is not None:
+        rev = np.asarray(forced_rev, dtype=bool)
     idx = s[:, None] + np.arange(L, dtype=np.int64)[None, :]
     seq = np.where(hap[:, None], haps[1][idx], haps[0][idx])
     # substitutions (in genome orientation, before strand flip)
@@ -308,6 +324,9 @@ def simulate_reads(
     lo_q = (np.uint8(ord("#")) + ((rq >> U64(16)) % U64(21)).astype(np.uint8))         # '#'..'7'
     is_low = ((rq >> U64(32)) < U64(int(lowq_prob * (1 << 32)))) & (np.arange(L)[None, :] < lowq_chars)
     qual = np.where(is_low, lo_q, hi_q)
+    if qual_alphabet is not None:
+        qa = np.frombuffer(qual_alphabet, dtype=np.uint8)
+        qual = qa[((rq >> U64(24)) % U64(qa.size)).astype(np.int64)]
 
     rec_len = 2 + id_width + 1 + L + 3 + L + 1
     out = np.empty((n_reads, rec_len), dtype=np.uint8)
