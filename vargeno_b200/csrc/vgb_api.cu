@@ -1,0 +1,421 @@
+// vgb_api.cu -- the C ABI (include/vgb200.h): context, chunk pipeline, statistics.
+#include <cstdarg>
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "vgb_internal.h"
+
+namespace vgb {
+
+thread_local std::string g_create_err;
+
+int set_err(vgb_ctx *c, int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (c) c->err = buf; else g_create_err = buf;
+	return code;
+}
+
+static void collect_times(vgb_ctx *c, int slot);
+
+}  // namespace vgb
+
+using namespace vgb;
+
+extern "C" {
+
+int vgb_abi_version(void) { return VGB_ABI_VERSION; }
+
+const char *vgb_last_error(const vgb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int vgb_nccl_unique_id(void *out128)
+{
+	std::string err;
+	const int rc = nccl_unique_id(out128, err);
+	if (rc) g_create_err = err;
+	return rc;
+}
+
+int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
+{
+	if (!out || !cfg) return set_err(nullptr, VGB_E_ARG, "null argument");
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return set_err(nullptr, VGB_E_CUDA, "no CUDA device (%s): libvgb200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	if (cfg->device < 0 || cfg->device >= ndev) return set_err(nullptr, VGB_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+	if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return set_err(nullptr, VGB_E_ARG, "bad world_size / rank");
+	if (cfg->world_size > 1 && !cfg->nccl_unique_id) return set_err(nullptr, VGB_E_ARG, "world_size > 1 needs an NCCL unique id");
+	cudaDeviceProp prop;
+	if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+		return set_err(nullptr, VGB_E_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e));
+	if (prop.major < 10) return set_err(nullptr, VGB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+	vgb_ctx *c = new vgb_ctx();
+	c->cfg = *cfg;
+	c->device = cfg->device;
+	c->sm_count = prop.multiProcessorCount;
+	c->max_chunk_bytes = cfg->max_chunk_bytes ? cfg->max_chunk_bytes : (256ull << 20);
+	if (c->max_chunk_bytes > 0xFFFFFF00ull) { delete c; return set_err(nullptr, VGB_E_ARG, "max_chunk_bytes must stay below 4 GiB (32-bit line offsets)"); }
+	c->max_chunk_bytes = (c->max_chunk_bytes + 4095) & ~4095ull;
+#define CK(call) do { if ((e = (call)) != cudaSuccess) { set_err(nullptr, VGB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e)); vgb_ctx_destroy(c); return VGB_E_CUDA; } } while (0)
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
+	CK(cudaMalloc((void **)&c->d_stats, sizeof(DevStats)));
+	CK(cudaMemset(c->d_stats, 0, sizeof(DevStats)));
+	CK(cudaMalloc((void **)&c->d_tables, (64 * 64 * 3 + 127) * sizeof(double)));
+	{
+		std::vector<double> t(64 * 64 * 3 + 127);
+		build_call_tables(t.data(), t.data() + 64 * 64 * 3);
+		CK(cudaMemcpy(c->d_tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+	}
+	const uint64_t nblk = c->max_chunk_bytes / 4096 + 2;
+	for (int s = 0; s < 2; s++) {
+		Chunk &k = c->chunk[s];
+		CK(cudaMalloc((void **)&k.d_text, c->max_chunk_bytes + 64));
+		CK(cudaMalloc((void **)&k.d_line_start, (c->max_chunk_bytes / 2 + 16) * 4));
+		CK(cudaMalloc((void **)&k.d_blk_counts, (2 * nblk + 64) * 4));
+		CK(cudaMalloc((void **)&k.d_meta, 64));
+		CK(cudaMemset(k.d_meta, 0, 64));
+		CK(cudaEventCreateWithFlags(&k.copied, cudaEventDisableTiming));
+		CK(cudaEventCreate(&k.done));
+		CK(cudaEventCreate(&k.t0));
+		CK(cudaEventCreate(&k.t1));
+	}
+#undef CK
+	if (cfg->world_size > 1) {
+		const int rc = nccl_init(c);
+		if (rc) { g_create_err = c->err; vgb_ctx_destroy(c); return rc; }
+	}
+	*out = c;
+	return VGB_OK;
+}
+
+void vgb_ctx_destroy(vgb_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	nccl_destroy(c);
+	for (int i = 0; i < c->n_owned; i++) cudaFree(c->owned[i]);
+	for (int s = 0; s < 2; s++) {
+		Chunk &k = c->chunk[s];
+		cudaFree(k.d_text); cudaFree(k.d_line_start); cudaFree(k.d_blk_counts); cudaFree(k.d_meta);
+		if (k.h_pinned) cudaFreeHost(k.h_pinned);
+		if (k.copied) cudaEventDestroy(k.copied);
+		if (k.done) cudaEventDestroy(k.done);
+		if (k.t0) cudaEventDestroy(k.t0);
+		if (k.t1) cudaEventDestroy(k.t1);
+	}
+	cudaFree(c->d_stats); cudaFree(c->d_tables); cudaFree(c->d_trace);
+	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	delete c;
+}
+
+int vgb_index_upload(vgb_ctx *c, const vgb_index_view *view)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return index_upload(c, view);
+}
+
+int vgb_site_count(vgb_ctx *c, uint64_t *n)
+{
+	if (!c || !n) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
+	*n = c->ix.n_sites;
+	return VGB_OK;
+}
+
+int vgb_fetch_sites(vgb_ctx *c, uint32_t *pos, uint8_t *code, uint8_t *rf, uint8_t *af, uint64_t n)
+{
+	if (!c) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
+	if (n != c->ix.n_sites) return set_err(c, VGB_E_ARG, "n_sites mismatch");
+	cudaSetDevice(c->device);
+	if (n == 0) return VGB_OK;
+	if (pos) VGB_CUDA(c, cudaMemcpy(pos, c->d_site_pos, n * 4, cudaMemcpyDeviceToHost));
+	if (code) VGB_CUDA(c, cudaMemcpy(code, c->ix.site_code, n, cudaMemcpyDeviceToHost));
+	if (rf) VGB_CUDA(c, cudaMemcpy(rf, c->d_site_rf, n, cudaMemcpyDeviceToHost));
+	if (af) VGB_CUDA(c, cudaMemcpy(af, c->d_site_af, n, cudaMemcpyDeviceToHost));
+	return VGB_OK;
+}
+
+int vgb_pinned_buffer(vgb_ctx *c, int slot, char **ptr, uint64_t *cap)
+{
+	if (!c || slot < 0 || slot > 1 || !ptr) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	Chunk &k = c->chunk[slot];
+	if (!k.h_pinned) VGB_CUDA(c, cudaMallocHost((void **)&k.h_pinned, c->max_chunk_bytes));
+	VGB_CUDA(c, cudaEventSynchronize(k.copied));       // the H2D copy out of this buffer has finished
+	*ptr = k.h_pinned;
+	if (cap) *cap = c->max_chunk_bytes;
+	return VGB_OK;
+}
+
+}  // extern "C"
+
+namespace vgb {
+
+static void collect_times(vgb_ctx *c, int slot)
+{
+	Chunk &k = c->chunk[slot];
+	if (!k.busy) return;
+	cudaEventSynchronize(k.done);
+	float a = 0, b = 0;
+	if (cudaEventElapsedTime(&a, k.t0, k.t1) == cudaSuccess) c->ms_parse += a;
+	if (cudaEventElapsedTime(&b, k.t1, k.done) == cudaSuccess) c->ms_geno += b;
+	k.busy = false;
+}
+
+static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_chunk, uint64_t nbytes, uint64_t first_read_id)
+{
+	if (!c) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "vgb_index_upload has not been called");
+	if (nbytes > c->max_chunk_bytes) return set_err(c, VGB_E_ARG, "chunk of %llu bytes exceeds max_chunk_bytes %llu", (unsigned long long)nbytes, (unsigned long long)c->max_chunk_bytes);
+	if (nbytes == 0) return VGB_OK;
+	cudaSetDevice(c->device);
+	const int slot = c->next_slot;
+	c->next_slot ^= 1;
+	Chunk &k = c->chunk[slot];
+	collect_times(c, slot);                            // waits until the previous chunk in this slot is done
+	char *own_text = k.d_text;
+	if (device_chunk) {
+		k.d_text = const_cast<char *>(device_chunk);   // resident input: no copy at all
+	} else {
+		VGB_CUDA(c, cudaMemcpyAsync(k.d_text, host_chunk, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+		VGB_CUDA(c, cudaEventRecord(k.copied, c->copy_stream));
+		VGB_CUDA(c, cudaStreamWaitEvent(c->stream, k.copied, 0));
+		if (host_chunk != k.h_pinned && host_chunk != c->chunk[slot ^ 1].h_pinned)
+			VGB_CUDA(c, cudaEventSynchronize(k.copied));   // caller's own memory: safe to reuse on return
+	}
+	VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));
+	int rc = fastq_index_lines(c, k, nbytes);
+	if (rc == VGB_OK) {
+		VGB_CUDA(c, cudaEventRecord(k.t1, c->stream));
+		if (c->cfg.flags & VGB_CFG_TRACE) {
+			// the trace is indexed by read ordinal: learn this chunk's read count and grow the buffer
+			uint32_t meta[4];
+			VGB_CUDA(c, cudaMemcpyAsync(meta, k.d_meta, 16, cudaMemcpyDeviceToHost, c->stream));
+			VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+			const uint64_t need = c->trace_n + meta[1];
+			if (need > c->trace_cap) {
+				const uint64_t cap = std::max<uint64_t>(need, c->trace_cap * 2 + 1024);
+				vgb_read_result *nt = nullptr;
+				VGB_CUDA(c, cudaMalloc((void **)&nt, cap * sizeof(vgb_read_result)));
+				if (c->trace_n) VGB_CUDA(c, cudaMemcpy(nt, c->d_trace, c->trace_n * sizeof(vgb_read_result), cudaMemcpyDeviceToDevice));
+				cudaFree(c->d_trace);
+				c->d_trace = nt; c->trace_cap = cap;
+			}
+			rc = geno_launch(c, k, nbytes, first_read_id);
+			c->trace_n = need;
+		} else {
+			rc = geno_launch(c, k, nbytes, first_read_id);
+		}
+	}
+	cudaEventRecord(k.done, c->stream);
+	k.busy = true;
+
+	if (device_chunk) k.d_text = own_text;
+	c->chunks++;
+	c->chunk_bytes += nbytes;
+	return rc;
+}
+
+}  // namespace vgb
+
+extern "C" {
+
+int vgb_submit_fastq(vgb_ctx *c, const char *chunk, uint64_t nbytes, uint64_t first_read_id)
+{
+	if (!chunk && nbytes) return c ? set_err(c, VGB_E_ARG, "null chunk") : VGB_E_ARG;
+	return submit_common(c, chunk, nullptr, nbytes, first_read_id);
+}
+
+int vgb_submit_fastq_device(vgb_ctx *c, const char *device_chunk, uint64_t nbytes, uint64_t first_read_id)
+{
+	if (!device_chunk && nbytes) return c ? set_err(c, VGB_E_ARG, "null chunk") : VGB_E_ARG;
+	return submit_common(c, nullptr, device_chunk, nbytes, first_read_id);
+}
+
+int vgb_sync(vgb_ctx *c)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	collect_times(c, 0);
+	collect_times(c, 1);
+	uint32_t bits = 0;
+	for (int s = 0; s < 2; s++) {
+		uint32_t meta[6] = { 0, 0, 0, 0, 0, 0 };
+		VGB_CUDA(c, cudaMemcpy(meta, c->chunk[s].d_meta, 24, cudaMemcpyDeviceToHost));
+		bits |= meta[3] | meta[5];
+	}
+	DevStats st;
+	VGB_CUDA(c, cudaMemcpy(&st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+	c->sticky_format |= bits;
+	if (c->sticky_format || st.bad_records)
+		return set_err(c, VGB_E_FORMAT, "FASTQ input violates the contract:%s%s%s (%llu bad records)",
+		               (c->sticky_format & 1) ? " truncated record (line count not a multiple of 4);" : "",
+		               (c->sticky_format & 2) ? " line longer than 1022 characters, base outside ACGTNacgtn or quality line too short;" : "",
+		               (c->sticky_format & 4) ? " too many lines for max_chunk_bytes;" : "", st.bad_records);
+	if (st.overflow_reads)
+		return set_err(c, VGB_E_OVERFLOW, "%llu reads produced more than 2000 hit contexts per dictionary (the reference overflows its arrays, src/qv.cc:709,728-729)", st.overflow_reads);
+	return VGB_OK;
+}
+
+int vgb_reset_counts(vgb_ctx *c)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	VGB_CUDA(c, cudaMemset(c->d_stats, 0, sizeof(DevStats)));
+	if (c->have_index && c->ix.n_sites) VGB_CUDA(c, cudaMemset(c->ix.cnt, 0, 2 * c->ix.n_sites * 4));
+	for (int s = 0; s < 2; s++) VGB_CUDA(c, cudaMemset(c->chunk[s].d_meta, 0, 64));
+	c->trace_n = 0; c->sticky_format = 0;
+	c->chunks = c->chunk_bytes = 0; c->ms_parse = c->ms_geno = 0; c->launches = 0;
+	return VGB_OK;
+}
+
+int vgb_fetch_read_results(vgb_ctx *c, vgb_read_result *out, uint64_t cap, uint64_t *n)
+{
+	if (!c || !n) return VGB_E_ARG;
+	if (!(c->cfg.flags & VGB_CFG_TRACE)) return set_err(c, VGB_E_ARG, "context was created without VGB_CFG_TRACE");
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	*n = c->trace_n;
+	const uint64_t m = std::min(cap, c->trace_n);
+	if (out && m) VGB_CUDA(c, cudaMemcpy(out, c->d_trace, m * sizeof(vgb_read_result), cudaMemcpyDeviceToHost));
+	return VGB_OK;
+}
+
+int vgb_lookup_kmers(vgb_ctx *c, const uint64_t *kmers, uint64_t n, vgb_hit *out)
+{
+	if (!c || (n && (!kmers || !out))) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return lookup_kmers(c, kmers, n, out);
+}
+
+int vgb_allreduce_pileup(vgb_ctx *c)
+{
+	if (!c) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
+	if (c->cfg.world_size == 1) return VGB_OK;
+	cudaSetDevice(c->device);
+	const int rc = nccl_allreduce_u32(c, c->ix.cnt, 2 * c->ix.n_sites);
+	if (rc) return rc;
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VGB_OK;
+}
+
+int vgb_fetch_pileup(vgb_ctx *c, uint32_t *ref_cnt, uint32_t *alt_cnt, uint64_t n_sites)
+{
+	if (!c || (n_sites && (!ref_cnt || !alt_cnt))) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return fetch_pileup(c, ref_cnt, alt_cnt, n_sites);
+}
+
+int vgb_call(vgb_ctx *c, uint8_t *gtype, double *conf, uint64_t n_sites)
+{
+	if (!c || (n_sites && (!gtype || !conf))) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return call_sites(c, gtype, conf, n_sites);
+}
+
+int vgb_counter_device_ptr(vgb_ctx *c, void **ptr, uint64_t *n_u32)
+{
+	if (!c || !ptr || !n_u32) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
+	*ptr = c->ix.cnt;
+	*n_u32 = 2 * c->ix.n_sites;
+	return VGB_OK;
+}
+
+int vgb_get_stats(vgb_ctx *c, vgb_stats *out)
+{
+	if (!c || !out) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	collect_times(c, 0);
+	collect_times(c, 1);
+	DevStats st;
+	VGB_CUDA(c, cudaMemcpy(&st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+	memset(out, 0, sizeof(*out));
+	out->reads = st.reads; out->skipped_n = st.skipped_n; out->passes = st.passes; out->placed = st.placed;
+	out->exact_lookups = st.exact_lookups; out->nbr_query_lookups = st.nbr_query_lookups; out->nbr_scan_reads = st.nbr_scan_reads;
+	out->bf_probes = st.bf_probes; out->lowq_kmers = st.lowq_kmers; out->events = st.events; out->pileup_incr = st.pileup_incr;
+	out->big_kmers = st.big_kmers; out->bad_records = st.bad_records;
+	out->chunks = c->chunks; out->chunk_bytes = c->chunk_bytes;
+	out->gpu_ms_parse = c->ms_parse; out->gpu_ms_geno = c->ms_geno; out->kernel_launches = c->launches;
+	return VGB_OK;
+}
+
+int vgb_probe_bench(vgb_ctx *c, uint64_t n, int mode, uint64_t seed, int repeats, double *ms, uint64_t *found)
+{
+	if (!c || !ms || !found || n == 0) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return probe_bench(c, n, mode, seed, repeats, ms, found);
+}
+
+int vgb_random_sector_bench(vgb_ctx *c, uint64_t bytes, uint64_t n_loads, int repeats, double *gbs)
+{
+	if (!c || !gbs || bytes < 4096 || n_loads == 0) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return random_sector_bench(c, bytes, n_loads, repeats, gbs);
+}
+
+int vgb_synth_reads_device(vgb_ctx *c, const uint8_t *hap0, const uint8_t *hap1, uint64_t genome_len, const uint64_t *cstart,
+                           const uint64_t *clen, uint32_t n_contigs, uint64_t n_reads, uint32_t read_len, uint64_t seed,
+                           uint64_t first_id, uint32_t id_width, double sub_rate, double lowq_prob, uint32_t lowq_chars,
+                           char *out, uint64_t out_cap)
+{
+	if (!c || !hap0 || !hap1 || !cstart || !clen || !out || n_contigs == 0) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return synth_reads(c, hap0, hap1, genome_len, cstart, clen, n_contigs, n_reads, read_len, seed, first_id, id_width, sub_rate,
+	                   lowq_prob, lowq_chars, out, out_cap);
+}
+
+void *vgb_device_alloc(vgb_ctx *c, uint64_t bytes)
+{
+	if (!c) return nullptr;
+	cudaSetDevice(c->device);
+	void *p = nullptr;
+	if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { set_err(c, VGB_E_CUDA, "cudaMalloc(%llu) failed", (unsigned long long)bytes); return nullptr; }
+	return p;
+}
+
+void vgb_device_free(vgb_ctx *c, void *p)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaFree(p);
+}
+
+int vgb_memcpy_d2h(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	return VGB_OK;
+}
+
+int vgb_memcpy_h2d(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+	return VGB_OK;
+}
+
+}  // extern "C"

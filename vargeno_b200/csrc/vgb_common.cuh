@@ -1,0 +1,181 @@
+// vgb_common.cuh -- device-side view of the index and the probe primitives shared by all kernels.
+//
+// HBM layout.  Everything the per-read kernel touches at random is sized so that ONE probe
+// step is ONE aligned load that cannot straddle a 32-byte DRAM sector:
+//   RefEntry  8 B  {kmer_lo32, posx}      replaces struct kmer_entry (9 B packed, src/vartype.h:64-73)
+//   SnpEntry 16 B  {lo40|info|flag, pos, alt|rf|af}   replaces struct snp_kmer_entry (11 B packed, :75-80)
+//   PileBlk  16 B  {64-position site bitmap, rank}    replaces the dense 4 B/position packed_pileup_entry (:82-89)
+// Entry RANK is preserved (arrays stay sorted by k-mer) because the reference's small-block scan is rank-strided.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vgb {
+
+constexpr uint32_t POS_AMBIGUOUS = 0xFFFFFFFFu;      // src/vartype.h:33
+constexpr int AUX_COLS = 10;                          // src/vartype.h:93
+constexpr uint32_t BLOCK_SIZE_THRESHOLD = 100;        // src/vartype.h:103
+constexpr int MAX_COV = 63;                           // src/vartype.h:27
+constexpr int QUALITY_SCORE = '8';                    // src/vartype.h:17
+constexpr uint32_t REF_STRIDE = 9;                    // sizeof(struct kmer_entry): the stride of the reference's scan (F13)
+constexpr uint32_t SNP_STRIDE = 11;                   // sizeof(struct snp_kmer_entry)
+constexpr uint32_t MAX_HITS = 2000;                   // src/qv.cc:709
+constexpr uint32_t NO_MOD = 0xFFu;                    // stands for NO_MODIFICATION (src/qv.cc:710)
+
+struct __align__(8) RefEntry {
+	uint32_t lo;    // LO32(kmer)
+	uint32_t posx;  // pos if < amb_lo; 0xFFFFFFFF = POS_AMBIGUOUS; else aux row = 0xFFFFFFFE - posx
+};
+
+struct __align__(16) SnpEntry {
+	uint64_t key;   // bits 0..39 LO40(kmer) | snp_info << 40 | ambig_flag << 48
+	uint32_t pos;   // pos, or aux row when flag == 1
+	uint32_t extra; // alt base (kmer_get_base(kmer, SNP_INFO_POS)) | ref_freq << 8 | alt_freq << 16
+};
+
+struct __align__(16) PileBlk {
+	uint64_t bits;  // bit b: position 64*blk + b has ref != 0 || alt != 0 in the static pileup
+	uint32_t rank;  // number of such positions before this block = site id of its first site
+	uint32_t pad;
+};
+
+struct DevIndex {
+	const RefEntry *ref;        uint64_t n_ref;
+	const uint32_t *ref_jg;     // 2^32 + 1 entries: ref_jg[h] = #entries with HI32 < h (src/qv.cc:539-584)
+	const uint32_t *ref_aux;    uint32_t n_ref_aux; uint32_t amb_lo;
+	const SnpEntry *snp;        uint64_t n_snp;
+	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678)
+	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
+	const uint32_t *ref_bf;     uint64_t ref_bf_bits; uint64_t ref_bf_nw32;
+	const uint32_t *snp_bf;     uint64_t snp_bf_bits; uint64_t snp_bf_nw32;
+	const PileBlk  *pile;       uint64_t pile_len;   // positions [0, pile_len)
+	const uint8_t  *site_code;  // ref | alt << 2 per site
+	uint64_t n_sites;
+	uint32_t *cnt;              // [2 * n_sites]: {ref_cnt, alt_cnt} per site, unsaturated
+};
+
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x)   // src/generate_bf.h:126-131
+{
+	x = ((x >> 16) ^ x) * 0x45d9f3bu;
+	x = ((x >> 16) ^ x) * 0x45d9f3bu;
+	x = (x >> 16) ^ x;
+	return x;
+}
+__host__ __device__ __forceinline__ uint64_t hash40(uint64_t x)   // src/generate_bf.h:138-143
+{
+	x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+	x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+	x = x ^ (x >> 31);
+	return x;
+}
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) { return hash40(x); }
+
+// digest of one hit context; must equal vgo_ctx_digest (oracle/vg_oracle.c) -- used only by the trace
+__host__ __device__ __forceinline__ uint64_t ctx_digest(uint32_t list_id, uint32_t position, uint32_t kmer_pos, uint64_t kmer, uint32_t mod)
+{
+	uint64_t h = mix64(kmer + 0x9E3779B97F4A7C15ull);
+	h = mix64(h ^ (((uint64_t)position << 32) | kmer_pos));
+	h = mix64(h ^ (((uint64_t)mod << 8) | (uint64_t)list_id));
+	return h;
+}
+
+#ifdef __CUDACC__
+// BloomFilter::check_value, value_range 32 (src/generate_bf.h:112-114)
+__device__ __forceinline__ bool bf_ref(const DevIndex &ix, uint32_t lo32)
+{
+	uint64_t bit = hash32(lo32);
+	if (ix.ref_bf_bits <= 0xFFFFFFFFull) bit %= ix.ref_bf_bits;   // 9.6e9 bits in practice: the modulo is the identity
+	const uint64_t w = bit >> 5;
+	if (w >= ix.ref_bf_nw32) return false;
+	return (__ldg(ix.ref_bf + w) >> (bit & 31)) & 1u;
+}
+// value_range 40 (src/generate_bf.h:115-116)
+__device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
+{
+	const uint64_t bit = hash40(lo40) % ix.snp_bf_bits;
+	const uint64_t w = bit >> 5;
+	if (w >= ix.snp_bf_nw32) return false;
+	return (__ldg(ix.snp_bf + w) >> (bit & 31)) & 1u;
+}
+
+// jumpgate pair of the HI32 block (src/qv.cc:219-233, check_block_size :242-264)
+__device__ __forceinline__ void ref_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
+{
+	const uint64_t h = kmer >> 32;
+	lo = __ldg(ix.ref_jg + h);
+	hi = __ldg(ix.ref_jg + h + 1);
+}
+__device__ __forceinline__ void snp_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
+{
+	const uint64_t h = kmer >> 40;
+	lo = __ldg(ix.snp_jg + h);
+	hi = __ldg(ix.snp_jg + h + 1);
+}
+
+// query_ref_dict (src/qv.cc:206-240) inside an already known block: rank of the entry or -1
+__device__ __forceinline__ int64_t ref_find_in_block(const DevIndex &ix, uint32_t key_lo, uint32_t lo, uint32_t hi, uint32_t &posx)
+{
+	while (hi - lo > 4) {
+		const uint32_t mid = lo + ((hi - lo) >> 1);
+		const uint32_t v = __ldg(&ix.ref[mid].lo);
+		if (v <= key_lo) lo = mid; else hi = mid;
+	}
+	for (uint32_t i = lo; i < hi; i++) {
+		const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ix.ref + i));
+		if (e.x == key_lo) { posx = e.y; return (int64_t)i; }
+	}
+	return -1;
+}
+__device__ __forceinline__ int64_t ref_query(const DevIndex &ix, uint64_t kmer, uint32_t &posx)
+{
+	uint32_t lo, hi;
+	ref_block(ix, kmer, lo, hi);
+	if (lo >= hi) return -1;
+	return ref_find_in_block(ix, (uint32_t)kmer, lo, hi, posx);
+}
+
+// query_snp_dict (src/qv.cc:385-411)
+__device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_t key_lo40, uint32_t lo, uint32_t hi, SnpEntry &out)
+{
+	const uint64_t M40 = 0xFFFFFFFFFFull;
+	while (hi - lo > 2) {
+		const uint32_t mid = lo + ((hi - lo) >> 1);
+		const uint64_t v = __ldg(&ix.snp[mid].key) & M40;
+		if (v <= key_lo40) lo = mid; else hi = mid;
+	}
+	for (uint32_t i = lo; i < hi; i++) {
+		const uint4 e = __ldg(reinterpret_cast<const uint4 *>(ix.snp + i));
+		const uint64_t key = ((uint64_t)e.y << 32) | e.x;
+		if ((key & M40) == key_lo40) { out.key = key; out.pos = e.z; out.extra = e.w; return (int64_t)i; }
+	}
+	return -1;
+}
+__device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
+{
+	uint32_t lo, hi;
+	snp_block(ix, kmer, lo, hi);
+	if (lo >= hi) return -1;
+	return snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, lo, hi, out);
+}
+
+__device__ __forceinline__ uint32_t snp_info_of(const SnpEntry &e) { return (uint32_t)(e.key >> 40) & 0xFFu; }
+__device__ __forceinline__ uint32_t snp_flag_of(const SnpEntry &e) { return (uint32_t)(e.key >> 48) & 0xFFu; }
+
+// static pileup: is position p a site (ref != 0 || alt != 0)?  -- the veto test of src/qv.cc:990-991
+__device__ __forceinline__ bool pile_nonzero(const DevIndex &ix, uint64_t p)
+{
+	if (p >= ix.pile_len) return false;
+	const uint64_t bits = __ldg(&ix.pile[p >> 6].bits);
+	return (bits >> (p & 63)) & 1ull;
+}
+
+// one_hamming_distance_32/64 (src/qv.cc:267-312): x != 0 confined to one 2-bit slot -> slot index, else -1
+__device__ __forceinline__ int one_base_slot(uint64_t x)
+{
+	if (x == 0) return -1;
+	const int d = (__ffsll((long long)x) - 1) >> 1;
+	return ((x >> (2 * d)) <= 3ull) ? d : -1;
+}
+#endif
+
+}  // namespace vgb

@@ -1,0 +1,118 @@
+// vgb_internal.h -- host-side context shared by the translation units of libvgb200.so
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/vgb200.h"
+#include "vgb_common.cuh"
+
+namespace vgb {
+
+struct DevStats {   // device-resident counters, one cache line apart from nothing important; fetched by vgb_get_stats
+	unsigned long long reads, skipped_n, passes, placed, exact_lookups, nbr_query_lookups, nbr_scan_reads, bf_probes,
+	    lowq_kmers, events, pileup_incr, big_kmers, bad_records, overflow_reads, freq_wrap_reads, first_error;
+};
+
+struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i+1 overlaps the kernels of chunk i)
+	char *d_text = nullptr;           // device copy of the text (owned unless external)
+	char *h_pinned = nullptr;         // pinned staging buffer handed out by vgb_pinned_buffer
+	uint32_t *d_line_start = nullptr; // [max_lines + 1] byte offset of each line start
+	uint32_t *d_blk_counts = nullptr; // newline count per 4 KiB tile, then its exclusive scan
+	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error
+	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr;
+	bool busy = false;
+};
+
+}  // namespace vgb
+
+struct vgb_ctx {
+	vgb_config cfg{};
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	std::string err;
+
+	// index (device)
+	vgb::DevIndex ix{};
+	bool have_index = false;
+	uint32_t *d_site_pos = nullptr;
+	uint8_t *d_site_rf = nullptr, *d_site_af = nullptr;
+	double *d_tables = nullptr;      // g[64][64][3] then poisson[127]
+	void *owned[64] = {};            // device allocations freed at destroy
+	int n_owned = 0;
+
+	// reads
+	uint64_t max_chunk_bytes = 0;
+	vgb::Chunk chunk[2];
+	int next_slot = 0;
+	vgb::DevStats *d_stats = nullptr;
+	vgb_read_result *d_trace = nullptr;
+	uint64_t trace_cap = 0, trace_n = 0;
+	uint32_t sticky_format = 0;      // format error bits seen since the last reset
+	void *d_spill = nullptr;         // per-warp overflow area for hit contexts
+	uint32_t geno_grid = 0;
+
+	// host-side statistics
+	uint64_t chunks = 0, chunk_bytes = 0, launches = 0;
+	double ms_parse = 0, ms_geno = 0;
+	cudaEvent_t ev[4] = {};
+
+	// NCCL (dlopen)
+	void *nccl_comm = nullptr;
+};
+
+namespace vgb {
+
+int set_err(vgb_ctx *c, int code, const char *fmt, ...);
+extern thread_local std::string g_create_err;
+
+#define VGB_CUDA(c, call)                                                                        \
+	do {                                                                                         \
+		cudaError_t e__ = (call);                                                                \
+		if (e__ != cudaSuccess)                                                                  \
+			return vgb::set_err((c), VGB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+template <typename T>
+int dev_alloc(vgb_ctx *c, T **p, uint64_t count, bool own = true)
+{
+	void *q = nullptr;
+	cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+	if (e != cudaSuccess) return set_err(c, VGB_E_CUDA, "cudaMalloc(%llu bytes) failed: %s", (unsigned long long)(count * sizeof(T)), cudaGetErrorString(e));
+	*p = (T *)q;
+	if (own && c->n_owned < 64) c->owned[c->n_owned++] = q;
+	return VGB_OK;
+}
+
+// vgb_index.cu
+int index_upload(vgb_ctx *c, const vgb_index_view *v);
+// vgb_fastq.cu
+int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes);
+// vgb_geno.cu
+int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id);
+int geno_prepare(vgb_ctx *c);
+// vgb_call.cu
+int call_sites(vgb_ctx *c, uint8_t *gtype, double *conf, uint64_t n_sites);
+int fetch_pileup(vgb_ctx *c, uint32_t *ref_cnt, uint32_t *alt_cnt, uint64_t n_sites);
+void build_call_tables(double *g /*64*64*3*/, double *poisson /*127*/);   // vgb_tables.cpp (plain C++, glibc libm)
+// vgb_bench.cu
+int lookup_kmers(vgb_ctx *c, const uint64_t *kmers, uint64_t n, vgb_hit *out);
+int probe_bench(vgb_ctx *c, uint64_t n, int mode, uint64_t seed, int repeats, double *ms, uint64_t *found);
+int random_sector_bench(vgb_ctx *c, uint64_t bytes, uint64_t n_loads, int repeats, double *gbs);
+int synth_reads(vgb_ctx *c, const uint8_t *hap0, const uint8_t *hap1, uint64_t genome_len, const uint64_t *cstart,
+                const uint64_t *clen, uint32_t n_contigs, uint64_t n_reads, uint32_t read_len, uint64_t seed, uint64_t first_id,
+                uint32_t id_width, double sub_rate, double lowq_prob, uint32_t lowq_chars, char *out, uint64_t out_cap);
+// vgb_nccl.cpp
+int nccl_unique_id(void *out128, std::string &err);
+int nccl_init(vgb_ctx *c);
+int nccl_allreduce_u32(vgb_ctx *c, uint32_t *buf, uint64_t n);
+void nccl_destroy(vgb_ctx *c);
+
+// generic device exclusive scan over uint32 (vgb_scan.cuh users): out[i] = sum_{j<i} in[j]; returns total through d_total
+int exclusive_scan_u32(vgb_ctx *c, const uint32_t *d_in, uint32_t *d_out, uint64_t n, uint32_t *d_tmp /* >= n/2048+2 */, uint32_t *d_total);
+
+}  // namespace vgb
