@@ -125,6 +125,10 @@ class Genotyper:
             self._ck(self.L.vgb_submit_fastq(self.h, _lib.ptr(piece), piece.size, rid))
             rid += n
 
+    def submit_chunk(self, chunk: np.ndarray, first_read_id: int = 0) -> None:
+        """One vgb_submit_fastq call on a buffer that already starts and ends at record boundaries (no host parsing)."""
+        self._ck(self.L.vgb_submit_fastq(self.h, _lib.ptr(chunk), chunk.size, first_read_id))
+
     def pinned_buffer(self, slot: int) -> np.ndarray:
         p, cap = C.c_void_p(), C.c_uint64()
         self._ck(self.L.vgb_pinned_buffer(self.h, slot, C.byref(p), C.byref(cap)))

@@ -505,3 +505,49 @@ def load_index(prefix: str) -> Index:
             names.append(a)
             lens.append(int(b))
     return Index(ref, ref_aux, snp, snp_aux, rbits, rbf, sbits, sbf, names, lens)
+
+
+# --------------------------------------------------------------------------------------
+# array fast path for synthetic sets (bench.py): no FASTA / VCF text round trip
+# --------------------------------------------------------------------------------------
+def snplines_from_arrays(seqs: Sequence[np.ndarray], contig, pos0, ref_ascii, alt_ascii, freq1, freq2) -> SnpLines:
+    """Vectorised twin of parse_vcf_for_dict for well-formed bi-allelic ACGT records that all carry CAF
+    (what tools/synth.write_vcf emits without extra lines).  freq1 / freq2 are the two CAF numbers as printed."""
+    contig = np.asarray(contig, np.int32)
+    pos0 = np.asarray(pos0, np.int64)
+    keep = np.zeros(pos0.size, bool)
+    for ci in np.unique(contig):
+        m = np.flatnonzero(contig == ci)
+        s = seqs[int(ci)]
+        p = pos0[m]
+        ok = (p >= 32) & (p + 32 <= s.size)
+        if np.any(s[p[ok]] != np.asarray(ref_ascii)[m][ok]):
+            raise ValueError("REF does not match the reference sequence (reference exits, src/dictgen.c:666-672)")
+        isn = np.concatenate([[0], np.cumsum((_CODE[s] == 4).astype(np.int64))])
+        q = np.where(ok, p, 32)
+        nfree = (isn[q + 32] - isn[q - 32]) == 0            # bases index-32 .. index+31 (src/dictgen.c:756-765)
+        keep[m] = ok & nfree
+    keep &= np.asarray(ref_ascii) != np.asarray(alt_ascii)
+    f1 = (np.asarray(freq1, np.float64).astype(np.float32) * np.float32(255.0)).astype(np.int64) & 0xFF
+    f2 = (np.asarray(freq2, np.float64).astype(np.float32) * np.float32(255.0)).astype(np.int64) & 0xFF
+    return SnpLines(contig[keep], pos0[keep], _CODE[np.asarray(ref_ascii)][keep], _CODE[np.asarray(alt_ascii)][keep],
+                    f1[keep].astype(np.uint8), f2[keep].astype(np.uint8))
+
+
+def build_index_from_arrays(names: Sequence[str], seqs: Sequence[np.ndarray], contig, pos0, ref_ascii, alt_ascii,
+                            freq1, freq2) -> Index:
+    """Same Index as build_index(write_fasta(...), write_vcf(...)) for upper-case ACGTN contigs with bare names."""
+    ref, ref_aux, pck = build_ref_dict(seqs, want_kmers=True)
+    lines = snplines_from_arrays(seqs, contig, pos0, ref_ascii, alt_ascii, freq1, freq2)
+    snp, snp_aux = build_snp_dict(lines, seqs, pck)
+    ref_bf, _ = build_ref_bf(pck, False)
+    # BF-side filter (src/generate_bf.cc:224-241): position window, REF matches, REF != ALT, 32 bases before N-free
+    contig = np.asarray(contig, np.int32)
+    pos0 = np.asarray(pos0, np.int64)
+    ok = np.zeros(pos0.size, bool)
+    for ci in np.unique(contig):
+        m = contig == ci
+        ok[m] = (pos0[m] >= 32) & (pos0[m] + 32 <= seqs[int(ci)].size)
+    ok &= np.asarray(ref_ascii) != np.asarray(alt_ascii)
+    snp_bf = snp_bf_from_arrays(contig[ok], pos0[ok], pck)
+    return Index(ref, ref_aux, snp, snp_aux, REF_BF_BITS, ref_bf, SNP_BF_BITS, snp_bf, list(names), [int(s.size) for s in seqs])
