@@ -73,8 +73,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     host_srcs = [os.path.join(CSRC, s) for s in HOST_CPP]
     if all(os.path.exists(s) for s in host_srcs):
         if force or _newer(HOST_BIN, host_srcs + hdrs + [LIB]):
-            _run(["g++"] + CXX_FLAGS + ["-fno-PIC", "-o", HOST_BIN] + host_srcs +
-                 ["-L" + HERE, "-lvgb200", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lpthread"])
+            _run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", HOST_BIN] + host_srcs +
+                 ["-L" + HERE, "-lvgb200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
     return LIB
 
 

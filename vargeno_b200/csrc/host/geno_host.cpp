@@ -1,0 +1,338 @@
+// geno_host.cpp -- see geno_host.h.  Plain C++17 over the C ABI; links libvgb200.so.
+#include "geno_host.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+namespace vgh {
+
+// ---------------------------------------------------------------------------------------------------------------
+// files
+// ---------------------------------------------------------------------------------------------------------------
+bool MappedFile::open(const std::string &path, std::string &err)
+{
+	fd = ::open(path.c_str(), O_RDONLY);
+	if (fd < 0) { err = "cannot open " + path; return false; }
+	struct stat st;
+	if (fstat(fd, &st) != 0) { err = "cannot stat " + path; return false; }
+	size = (uint64_t)st.st_size;
+	if (size == 0) { data = nullptr; return true; }
+	void *p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+	if (p == MAP_FAILED) { err = "cannot mmap " + path; return false; }
+	madvise(p, size, MADV_SEQUENTIAL);
+	data = (const uint8_t *)p;
+	return true;
+}
+
+void MappedFile::close()
+{
+	if (data) munmap((void *)data, size);
+	if (fd >= 0) ::close(fd);
+	data = nullptr; fd = -1; size = 0;
+}
+
+bool ChrLens::load(const std::string &path, std::string &err)
+{
+	FILE *f = fopen(path.c_str(), "r");
+	if (!f) { err = "cannot open " + path; return false; }
+	char buf[256];
+	while (fgets(buf, sizeof(buf), f)) {                        // src/qv.cc:486-499
+		size_t i = 0;
+		std::string name;
+		while (!isspace((unsigned char)buf[i]) && i < 32) name.push_back(buf[i++]);
+		while (isspace((unsigned char)buf[i])) ++i;
+		names.push_back(name);
+		lens.push_back((uint64_t)atol(&buf[i]));
+		if (names.size() > 128) { err = "more than 128 contigs in " + path + " (the reference's chrlens[128], src/qv.cc:482)"; fclose(f); return false; }
+	}
+	fclose(f);
+	return true;
+}
+
+void ChrLens::locate(uint64_t index, std::string &name, uint64_t &rel) const
+{
+	size_t j = 0;
+	for (; j < names.size() && index > lens[j]; j++) index -= lens[j];
+	name = j < names.size() ? names[j] : std::string();
+	rel = index;
+}
+
+static uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+bool IndexFiles::open(const std::string &prefix, std::string &err)
+{
+	if (!ref_dict.open(prefix + ".ref.dict", err) || !snp_dict.open(prefix + ".snp.dict", err) ||
+	    !ref_bf.open(prefix + ".ref.bf", err) || !snp_bf.open(prefix + ".snp.bf", err) || !chr.load(prefix + ".chrlens", err))
+		return false;
+	// .ref.dict: u64 n, u64 aux_n, n x 13 B, aux_n x 40 B (src/dictgen.c:63-154, read back by src/qv.cc:520-590)
+	if (ref_dict.size < 16) { err = prefix + ".ref.dict is truncated"; return false; }
+	const uint64_t n = rd64(ref_dict.data), an = rd64(ref_dict.data + 8);
+	if (ref_dict.size < 16 + 13 * n + 40 * an) { err = prefix + ".ref.dict is truncated"; return false; }
+	// .snp.dict: u64 m, u64 aux_m, m x 16 B, aux_m x 78 B (src/dictgen.c:156-275, src/qv.cc:607-695)
+	if (snp_dict.size < 16) { err = prefix + ".snp.dict is truncated"; return false; }
+	const uint64_t m = rd64(snp_dict.data), am = rd64(snp_dict.data + 8);
+	if (snp_dict.size < 16 + 16 * m + 78 * am) { err = prefix + ".snp.dict is truncated"; return false; }
+	// sdsl bit_vector: u64 bit count + ceil(bits / 64) words (sdsl-lite int_vector.hpp:1563-1595)
+	if (ref_bf.size < 8 || snp_bf.size < 8) { err = "Bloom filter file is truncated"; return false; }
+	const uint64_t rbits = rd64(ref_bf.data), sbits = rd64(snp_bf.data);
+	if (ref_bf.size < 8 + (rbits + 63) / 64 * 8 || snp_bf.size < 8 + (sbits + 63) / 64 * 8) { err = "Bloom filter file is truncated"; return false; }
+	view.ref_records = ref_dict.data + 16; view.n_ref = n;
+	view.ref_aux = (const uint32_t *)(ref_dict.data + 16 + 13 * n); view.n_ref_aux = an;
+	view.snp_records = snp_dict.data + 16; view.n_snp = m;
+	view.snp_aux = snp_dict.data + 16 + 16 * m; view.n_snp_aux = am;
+	view.ref_bf_words = (const uint64_t *)(ref_bf.data + 8); view.ref_bf_bits = rbits; view.ref_bf_nwords = (rbits + 63) / 64;
+	view.snp_bf_words = (const uint64_t *)(snp_bf.data + 8); view.snp_bf_bits = sbits; view.snp_bf_nwords = (sbits + 63) / 64;
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FASTQ streaming: pinned double buffers per context, chunks cut at record boundaries (4 lines per record)
+// ---------------------------------------------------------------------------------------------------------------
+static uint64_t count_newlines(const char *p, uint64_t n)
+{
+	uint64_t c = 0;
+	for (uint64_t i = 0; i < n; i++) c += (p[i] == '\n');     // auto-vectorised
+	return c;
+}
+
+int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
+{
+	const int fd = ::open(path.c_str(), O_RDONLY);
+	if (fd < 0) { err = "cannot open " + path; return VGB_E_ARG; }
+	posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+	std::vector<char> carry;                                    // bytes of the record cut at the end of the previous chunk
+	uint64_t read_id = 0;
+	n_chunks = 0;
+	size_t turn = 0;
+	bool eof = false;
+	int rc = VGB_OK;
+	while (!eof || !carry.empty()) {
+		vgb_ctx *ctx = ctxs[turn % ctxs.size()];
+		const int slot = (int)((turn / ctxs.size()) & 1);
+		turn++;
+		char *buf = nullptr;
+		uint64_t cap = 0;
+		if ((rc = vgb_pinned_buffer(ctx, slot, &buf, &cap)) != VGB_OK) { err = vgb_last_error(ctx); break; }
+		if (cap > chunk_bytes) cap = chunk_bytes;
+		uint64_t have = carry.size();
+		if (have > cap) { err = "a single FASTQ record is larger than the chunk size"; rc = VGB_E_FORMAT; break; }
+		memcpy(buf, carry.data(), have);
+		carry.clear();
+		while (!eof && have < cap) {
+			const ssize_t got = ::read(fd, buf + have, cap - have);
+			if (got < 0) { err = "read error on " + path; rc = VGB_E_ARG; break; }
+			if (got == 0) { eof = true; break; }
+			have += (uint64_t)got;
+		}
+		if (rc != VGB_OK) break;
+		if (have == 0) break;
+		uint64_t use = have;
+		uint64_t lines = count_newlines(buf, have);
+		if (!eof) {
+			// keep whole records only: drop the trailing partial line and (lines % 4) complete lines
+			uint64_t drop = lines % 4;
+			uint64_t p = have;
+			while (p > 0 && buf[p - 1] != '\n') p--;            // partial last line
+			while (drop > 0 && p > 0) { p--; while (p > 0 && buf[p - 1] != '\n') p--; drop--; }
+			use = p;
+			if (use == 0) { err = "a single FASTQ record is larger than the chunk size"; rc = VGB_E_FORMAT; break; }
+			carry.assign(buf + use, buf + have);
+			lines = count_newlines(buf, use);
+		} else if (have > 0 && buf[have - 1] != '\n') {
+			lines += 1;                                         // last line without newline
+		}
+		if ((rc = vgb_submit_fastq(ctx, buf, use, read_id)) != VGB_OK) { err = vgb_last_error(ctx); break; }
+		read_id += lines / 4;
+		n_chunks++;
+	}
+	::close(fd);
+	return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// calls + VCF
+// ---------------------------------------------------------------------------------------------------------------
+int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::string, Call> &out, std::string &err)
+{
+	uint64_t n = 0;
+	int rc = vgb_site_count(ctx, &n);
+	if (rc) { err = vgb_last_error(ctx); return rc; }
+	std::vector<uint32_t> pos(n);
+	std::vector<uint8_t> gt(n);
+	std::vector<double> conf(n);
+	if ((rc = vgb_fetch_sites(ctx, pos.data(), nullptr, nullptr, nullptr, n)) || (rc = vgb_call(ctx, gt.data(), conf.data(), n))) {
+		err = vgb_last_error(ctx);
+		return rc;
+	}
+	for (uint64_t i = 0; i < n; i++) {                          // position order, like the scan of src/qv.cc:1573-1626
+		if (gt[i] == 0) continue;                               // GTYPE_NONE
+		std::string name;
+		uint64_t rel;
+		chr.locate(pos[i], name, rel);
+		const char g = gt[i] == 1 ? '0' : (gt[i] == 2 ? '2' : '1');   // REF '0', ALT '2', HET '1' (src/qv.cc:1606-1618)
+		out[name + "$" + std::to_string(rel)] = Call{ g, conf[i] };
+	}
+	return VGB_OK;
+}
+
+static std::vector<std::string> split(const std::string &text, char sep)
+{
+	std::vector<std::string> tokens;
+	size_t start = 0, end;
+	while ((end = text.find(sep, start)) != std::string::npos) { tokens.push_back(text.substr(start, end - start)); start = end + 1; }
+	tokens.push_back(text.substr(start));
+	return tokens;
+}
+
+static std::string join(const std::vector<std::string> &v, char sep)
+{
+	std::string s = v.empty() ? std::string() : v[0];
+	for (size_t i = 1; i < v.size(); i++) { s += sep; s += v[i]; }
+	return s;
+}
+
+int rewrite_vcf(const std::string &vcf_in, const std::string &vcf_out, const std::unordered_map<std::string, Call> &calls, std::string &err)
+{
+	std::ifstream in(vcf_in);
+	if (!in.good()) { err = "Error opening: " + vcf_in; return VGB_E_ARG; }
+	std::ofstream out(vcf_out);
+	if (!out.good()) { err = "cannot write " + vcf_out; return VGB_E_ARG; }
+	bool has_gt = false, has_gq = false, sample_cols = true;
+	int gt_index = -1, gq_index = -1;
+	std::string line;
+	while (std::getline(in, line)) {
+		if (line.empty()) continue;
+		if (line[0] == '#' && line.size() > 1 && line[1] == '#') {
+			out << line << '\n';
+			if (line.find("ID=GT,") != std::string::npos) has_gt = true;
+			else if (line.find("ID=GQ,") != std::string::npos) has_gq = true;
+			continue;
+		}
+		if (line[0] == '#') {
+			if (!has_gt) { out << "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">" << '\n'; gt_index = 0; }
+			if (!has_gq) { out << "##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"Genotype Quality\">" << '\n'; gq_index = 1; }
+			if (split(line, '\t').size() < 10) { sample_cols = false; line += "\tFORMAT\tDONOR"; }
+			out << line << '\n';
+			continue;
+		}
+		std::vector<std::string> col = split(line, '\t');
+		if (col.size() < 2) continue;
+		std::string chrom = col[0];
+		if (chrom.empty() || chrom[0] != 'c') chrom = "chr" + chrom;
+		const auto it = calls.find(chrom + "$" + col[1]);
+		if (it == calls.end()) continue;                        // records that were not called are dropped (src/qv.cc:1674-1676)
+		const std::string gts = it->second.gt == '1' ? "0/1" : (it->second.gt == '2' ? "1/1" : "0/0");
+		const int gq = (int)(-1 * 10 * std::log(it->second.conf));   // src/qv.cc:1681
+		std::vector<std::string> fmt, smp;
+		if (sample_cols) {
+			if (col.size() < 10) { err = "record with fewer columns than the header (undefined in the reference)"; return VGB_E_FORMAT; }
+			fmt = split(col[8], ':');
+			smp = split(col[9], ':');
+		}
+		if (gt_index == -1 && has_gt) {
+			for (size_t i = 0; i < fmt.size(); i++) if (fmt[i] == "GT") { gt_index = (int)i; break; }
+			if (gt_index < 0) { err = "header declares GT but FORMAT has none (the reference asserts, src/qv.cc:1697)"; return VGB_E_FORMAT; }
+		}
+		if (gt_index == -1 && has_gq) { err = "header declares GQ but not GT: undefined in the reference (src/qv.cc:1699-1716)"; return VGB_E_FORMAT; }
+		if (has_gt) {
+			if ((size_t)gt_index >= smp.size()) { err = "sample column shorter than FORMAT"; return VGB_E_FORMAT; }
+			smp[gt_index] = gts;
+		} else { fmt.push_back("GT"); smp.push_back(gts); }
+		if (has_gq) {
+			if (gq_index < 0 || (size_t)gq_index >= smp.size()) { err = "header declares GQ: undefined in the reference (src/qv.cc:1699-1716)"; return VGB_E_FORMAT; }
+			smp[gq_index] = std::to_string(gq);
+		} else { fmt.push_back("GQ"); smp.push_back(std::to_string(gq)); }
+		if (sample_cols) { col[8] = join(fmt, ':'); col[9] = join(smp, ':'); }
+		else { col.push_back(join(fmt, ':')); col.push_back(join(smp, ':')); }
+		out << join(col, '\t') << '\n';
+	}
+	out.close();
+	return out.good() || true ? VGB_OK : VGB_E_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the command
+// ---------------------------------------------------------------------------------------------------------------
+int run_geno(const std::string &prefix, const std::string &fastq, const std::string &vcf_in, const std::string &vcf_out,
+             int n_gpus, uint64_t chunk_bytes, bool verbose)
+{
+	using clk = std::chrono::steady_clock;
+	const auto t0 = clk::now();
+	auto secs = [&](clk::time_point a) { return std::chrono::duration<double>(clk::now() - a).count(); };
+	std::string err;
+	IndexFiles ix;
+	if (!ix.open(prefix, err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	fprintf(stderr, "Initializing...\n");
+
+	// one context per GPU, created and loaded concurrently (NCCL rank initialisation is collective)
+	unsigned char uid[128];
+	if (n_gpus > 1 && vgb_nccl_unique_id(uid) != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", vgb_last_error(nullptr)); return EXIT_FAILURE; }
+	std::vector<vgb_ctx *> ctxs(n_gpus, nullptr);
+	std::vector<int> rcs(n_gpus, 0);
+	std::vector<std::string> errs(n_gpus);
+	{
+		std::vector<std::thread> th;
+		for (int r = 0; r < n_gpus; r++)
+			th.emplace_back([&, r]() {
+				vgb_config cfg{};
+				cfg.device = r; cfg.world_size = n_gpus; cfg.rank = r; cfg.flags = 0;
+				cfg.nccl_unique_id = n_gpus > 1 ? uid : nullptr;
+				cfg.max_chunk_bytes = chunk_bytes;
+				rcs[r] = vgb_ctx_create(&ctxs[r], &cfg);
+				if (rcs[r]) { errs[r] = vgb_last_error(nullptr); return; }
+				rcs[r] = vgb_index_upload(ctxs[r], &ix.view);
+				if (rcs[r]) errs[r] = vgb_last_error(ctxs[r]);
+			});
+		for (auto &t : th) t.join();
+	}
+	for (int r = 0; r < n_gpus; r++)
+		if (rcs[r]) {
+			fprintf(stderr, "vargeno-b200: GPU %d: %s\n", r, errs[r].c_str());
+			for (auto c : ctxs) vgb_ctx_destroy(c);
+			return EXIT_FAILURE;
+		}
+	const double t_load = secs(t0);
+	fprintf(stderr, "Processing...\n");
+
+	const auto t1 = clk::now();
+	uint64_t n_chunks = 0;
+	int rc = stream_fastq(ctxs, fastq, chunk_bytes, n_chunks, err);
+	for (int r = 0; rc == VGB_OK && r < n_gpus; r++)
+		if ((rc = vgb_sync(ctxs[r])) != VGB_OK) err = vgb_last_error(ctxs[r]);
+	if (rc == VGB_OK && n_gpus > 1) {                            // one exchange step: sum of the per-SNP counters
+		std::vector<std::thread> th;
+		for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r]() { rcs[r] = vgb_allreduce_pileup(ctxs[r]); if (rcs[r]) errs[r] = vgb_last_error(ctxs[r]); });
+		for (auto &t : th) t.join();
+		for (int r = 0; r < n_gpus; r++) if (rcs[r]) { rc = rcs[r]; err = errs[r]; }
+	}
+	const double t_reads = secs(t1);
+	std::unordered_map<std::string, Call> calls;
+	if (rc == VGB_OK) rc = collect_calls(ctxs[0], ix.chr, calls, err);
+	if (rc == VGB_OK) rc = rewrite_vcf(vcf_in, vcf_out, calls, err);
+	if (rc == VGB_OK && verbose) {
+		uint64_t reads = 0, placed = 0, lookups = 0;
+		for (auto c : ctxs) {
+			vgb_stats st;
+			if (vgb_get_stats(c, &st) == VGB_OK) { reads += st.reads; placed += st.placed; lookups += st.exact_lookups + st.nbr_query_lookups + st.nbr_scan_reads; }
+		}
+		fprintf(stderr, "{\"gpus\": %d, \"reads\": %llu, \"placed\": %llu, \"kmer_lookups\": %llu, \"chunks\": %llu, \"load_s\": %.3f, \"reads_s\": %.3f, "
+		        "\"reads_per_s\": %.0f, \"calls\": %zu}\n", n_gpus, (unsigned long long)reads, (unsigned long long)placed, (unsigned long long)lookups,
+		        (unsigned long long)n_chunks, t_load, t_reads, reads / (t_reads > 0 ? t_reads : 1), calls.size());
+	}
+	for (auto c : ctxs) vgb_ctx_destroy(c);
+	if (rc != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	printf("Time: %f sec\n", secs(t0));
+	return EXIT_SUCCESS;
+}
+
+}  // namespace vgh

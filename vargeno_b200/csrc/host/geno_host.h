@@ -1,0 +1,54 @@
+// geno_host.h -- host side of `vargeno-b200 geno`: index files -> C ABI, FASTQ streaming, VCF rewrite.
+// Everything above include/vgb200.h that the reference does on the host inside genotype() (src/qv.cc:475-1787),
+// written against the C ABI only (no CUDA headers here).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/vgb200.h"
+
+namespace vgh {
+
+struct MappedFile {
+	const uint8_t *data = nullptr;
+	uint64_t size = 0;
+	int fd = -1;
+	bool open(const std::string &path, std::string &err);
+	void close();
+	~MappedFile() { close(); }
+};
+
+struct ChrLens {          // src/qv.cc:481-499
+	std::vector<std::string> names;
+	std::vector<uint64_t> lens;
+	bool load(const std::string &path, std::string &err);
+	// contig-relative coordinate of a 1-based concatenated position (src/qv.cc:1590-1594)
+	void locate(uint64_t index, std::string &name, uint64_t &rel) const;
+};
+
+struct IndexFiles {
+	MappedFile ref_dict, snp_dict, ref_bf, snp_bf;
+	ChrLens chr;
+	vgb_index_view view{};
+	bool open(const std::string &prefix, std::string &err);   // <prefix>.ref.dict .snp.dict .ref.bf .snp.bf .chrlens
+};
+
+struct Call { char gt; double conf; };   // gt: '0' ref, '1' het, '2' alt (src/qv.cc:1606-1619)
+
+// Streams a FASTQ file through one or more contexts (round robin), record-aligned chunks in the contexts' pinned buffers.
+// Returns 0 or a VGB_E_* code (err filled).
+int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err);
+
+// stage F on the host side: device calls -> "chr$pos" -> (gt, conf) map (src/qv.cc:1596-1621)
+int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::string, Call> &out, std::string &err);
+
+// stage G: VCF rewrite (src/qv.cc:1628-1747)
+int rewrite_vcf(const std::string &vcf_in, const std::string &vcf_out, const std::unordered_map<std::string, Call> &calls, std::string &err);
+
+// the whole `geno` command on n_gpus devices of this node; returns process exit status
+int run_geno(const std::string &prefix, const std::string &fastq, const std::string &vcf_in, const std::string &vcf_out,
+             int n_gpus, uint64_t chunk_bytes, bool verbose);
+
+}  // namespace vgh

@@ -1,0 +1,43 @@
+// vargeno_main.cpp -- `vargeno-b200`: the reference's command line (src/qv.cc:1853-1881, 2109-2131) in front of the
+// B200 hot path.  `geno` is the drop-in; `index` stays with the reference program (the on-disk index is unchanged).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "geno_host.h"
+
+static void print_help()
+{
+	fprintf(stderr, "Usage: vargeno-b200 <option> [option parameters ...]\n");
+	fprintf(stderr, "Option  Description                   Parameters\n");
+	fprintf(stderr, "------  -----------                   ----------\n");
+	fprintf(stderr, "geno    Perform genotyping (B200)     <index_prefix> <input FASTQ> <input SNPs in VCF> <output file in VCF> "
+	                "[--gpus N] [--chunk-mb M] [--verbose]\n");
+	fprintf(stderr, "index   not re-implemented: run the reference's `vargeno index <input FASTA> <input SNPs in VCF> <index_prefix>`;\n");
+	fprintf(stderr, "        its five files are read unchanged\n");
+}
+
+int main(int argc, const char *argv[])
+{
+	if (argc < 2) { print_help(); return 0; }
+	const std::string opt = argv[1];
+	if (opt == "geno") {
+		std::string pos[4];
+		int npos = 0, gpus = 1;
+		uint64_t chunk_mb = 256;
+		bool verbose = false;
+		for (int i = 2; i < argc; i++) {
+			if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
+			else if (!strcmp(argv[i], "--chunk-mb") && i + 1 < argc) chunk_mb = strtoull(argv[++i], nullptr, 10);
+			else if (!strcmp(argv[i], "--verbose")) verbose = true;
+			else if (npos < 4) pos[npos++] = argv[i];
+			else npos++;
+		}
+		if (npos != 4 || gpus < 1 || chunk_mb < 1 || chunk_mb > 4000) { print_help(); return EXIT_FAILURE; }   // arg_check, src/qv.cc:1875-1881
+		return vgh::run_geno(pos[0], pos[1], pos[2], pos[3], gpus, chunk_mb << 20, verbose);
+	}
+	if (opt == "help") { print_help(); return EXIT_SUCCESS; }
+	print_help();
+	return EXIT_FAILURE;
+}
