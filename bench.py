@@ -116,6 +116,8 @@ def run_ours(args):
         uid = box[0]
     g = Genotyper(device=local, max_chunk_bytes=batch_bytes + 4096, world_size=world, rank=rank, nccl_unique_id=uid)
     g.upload_index(wl.index)
+    if world > 1:
+        g.allreduce()                       # NCCL connection set-up happens on the first collective: keep it out of the timed legs
 
     # synthetic reads, generated on the device (byte-identical twin of tools/synth.simulate_reads)
     h0 = g.dalloc(wl.haps[0].size)

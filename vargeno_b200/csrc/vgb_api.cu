@@ -65,6 +65,13 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 	if (c->max_chunk_bytes > 0xFFFFFF00ull) { delete c; return set_err(nullptr, VGB_E_ARG, "max_chunk_bytes must stay below 4 GiB (32-bit line offsets)"); }
 	c->max_chunk_bytes = (c->max_chunk_bytes + 4095) & ~4095ull;
 #define CK(call) do { if ((e = (call)) != cudaSuccess) { set_err(nullptr, VGB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e)); vgb_ctx_destroy(c); return VGB_E_CUDA; } } while (0)
+	{
+		// the probes of this path want single 32-byte sectors; ask L2 not to fetch 64 B per miss (profiles/r01_summary.md).
+		// VGB_L2_FETCH=64|128 restores a larger granularity for A/B measurements.
+		size_t gran = 32;
+		if (const char *e2 = getenv("VGB_L2_FETCH")) gran = (size_t)atoi(e2);
+		if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+	}
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));

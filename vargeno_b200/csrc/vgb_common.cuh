@@ -43,6 +43,10 @@ struct DevIndex {
 	const RefEntry *ref;        uint64_t n_ref;
 	const uint32_t *ref_jg;     // 2^32 + 1 entries: ref_jg[h] = #entries with HI32 < h (src/qv.cc:539-584)
 	const uint32_t *ref_aux;    uint32_t n_ref_aux; uint32_t amb_lo;
+	// secondary view of the reference dictionary keyed by LO32: all entries that share the lower 16 bases sit in one
+	// bucket, so the 48 upper-half Hamming-1 neighbours of a k-mer (src/qv.cc:1213-1298) are answered by one bucket read
+	const RefEntry *ref_by_lo;  // {HI32(kmer), posx}, bucket order unspecified
+	const uint32_t *ref_jg_lo;  // 2^32 entries: END of the bucket of LO32 == l (start = end of bucket l-1, 0 for l == 0)
 	const SnpEntry *snp;        uint64_t n_snp;
 	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678)
 	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
@@ -104,6 +108,11 @@ __device__ __forceinline__ void ref_block(const DevIndex &ix, uint64_t kmer, uin
 	const uint64_t h = kmer >> 32;
 	lo = __ldg(ix.ref_jg + h);
 	hi = __ldg(ix.ref_jg + h + 1);
+}
+__device__ __forceinline__ void ref_lo_bucket(const DevIndex &ix, uint32_t lo32, uint32_t &s, uint32_t &e)
+{
+	e = __ldg(ix.ref_jg_lo + lo32);
+	s = lo32 ? __ldg(ix.ref_jg_lo + lo32 - 1) : 0u;
 }
 __device__ __forceinline__ void snp_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {

@@ -155,7 +155,8 @@ __device__ __forceinline__ uint64_t substitute(uint64_t kmer, uint32_t d, uint32
 	return (kmer & ~(3ull << sh)) | (j << sh);
 }
 
-__global__ void __launch_bounds__(GW * 32) k_geno(const GenoArgs a)
+template <int MINB>
+__global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WarpSmem *ws = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
@@ -288,16 +289,33 @@ __global__ void __launch_bounds__(GW * 32) k_geno(const GenoArgs a)
 					const bool big = rB >= BLOCK_SIZE_THRESHOLD;                               // src/qv.cc:843,962
 					if (lane == 0) { st.lowq++; st.bf += 2; if (big) st.big++; }
 					// task segments (all bounds warp-uniform)
-					const uint32_t n0 = rb ? 48u : 0u;            // upper half, ref:  d = 16..31        (:1225)
+					// upper half, ref, d = 16..31 (:1225): the 48 substituted k-mers share LO32, so every dictionary k-mer
+					// that can answer one of those 48 queries sits in the LO32 bucket; one bucket walk replaces 48 probes
+					uint32_t bs = 0, be = 0;
+					if (rb) {
+						uint32_t v = 0;
+						if (lane < 2) v = (lane == 0) ? (((uint32_t)km) ? __ldg(ix.ref_jg_lo + (uint32_t)km - 1) : 0u) : __ldg(ix.ref_jg_lo + (uint32_t)km);
+						bs = __shfl_sync(0xffffffffu, v, 0);
+						be = __shfl_sync(0xffffffffu, v, 1);
+						if (lane == 0) st.nbrq += 48;             // the 48 reference queries this walk stands for
+					}
+					const uint32_t n0 = be - bs;
 					const uint32_t n1 = sb ? 36u : 0u;            // upper half, snp:  d = 20..31 if sb  (:1305-1307)
 					const uint32_t n2 = big ? 12u : 0u;           // upper half, snp:  d = 16..19 if big (:1305-1307)
 					const uint32_t n3 = big ? 48u : rB;           // lower half, ref: queries (:975) or strided scan (:358-373)
 					const uint32_t n4 = big ? 48u : sB;           // lower half, snp: queries (:977) or strided scan (:447-462)
 					const uint32_t e0 = n0, e1 = e0 + n1, e2 = e1 + n2, e3 = e2 + n3, e4 = e3 + n4;
 					for (uint32_t t = lane; t < e4; t += 32) {
-						if (t < e0 || (t >= e2 && t < e3 && big)) {                        // ref query
-							const uint32_t u = t < e0 ? t : t - e2;
-							const uint32_t d = (t < e0 ? 16u : 0u) + u / 3;
+						if (t < e0) {                                                        // LO32 bucket entry
+							const uint2 en = __ldg(reinterpret_cast<const uint2 *>(ix.ref_by_lo + bs + t));
+							const int sl = one_base_slot((uint64_t)(en.x ^ (uint32_t)(km >> 32)));
+							if (sl >= 0) {
+								const uint64_t nb = ((uint64_t)en.x << 32) | (uint32_t)km;
+								nbr_ref_events(ix, ws, spill, nb, en.y, 16u + (uint32_t)sl, offset, i, st);
+							}
+						} else if (t >= e2 && t < e3 && big) {                               // ref query (big mode, lower half)
+							const uint32_t u = t - e2;
+							const uint32_t d = u / 3;
 							const uint64_t nb = substitute(km, d, u % 3);
 							uint32_t posx;
 							st.nbrq++;
@@ -461,16 +479,24 @@ __global__ void __launch_bounds__(GW * 32) k_geno(const GenoArgs a)
 	}
 }
 
+typedef void (*geno_kernel_t)(const GenoArgs);
+static geno_kernel_t g_kernel = nullptr;
+
 int geno_prepare(vgb_ctx *c)
 {
+	// register budget variants of the same kernel: 4 CTAs/SM (64 regs), 6 (40 regs), 8 (32 regs); VGB_GENO_MINB picks one
+	int minb = 4;
+	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
+	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
+	g_kernel = k;
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
-	VGB_CUDA(c, cudaFuncSetAttribute(k_geno, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_geno, GW * 32, smem));
+	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
 	if (!c->d_spill) {
-		Event *sp;
+		Event *sp = nullptr;
 		int rc = dev_alloc(c, &sp, (uint64_t)c->geno_grid * GW * (EV_CAP - EV_SMEM));
 		if (rc) return rc;
 		c->d_spill = sp;
@@ -489,7 +515,7 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.stats = c->d_stats;
 	a.trace = c->d_trace ? c->d_trace + c->trace_n : nullptr;
 	a.spill = (Event *)c->d_spill;
-	k_geno<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+	g_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 	c->launches++;
 	VGB_CUDA(c, cudaGetLastError());
 	return VGB_OK;

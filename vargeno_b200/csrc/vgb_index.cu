@@ -183,7 +183,7 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *p) { return p[0] | (p[1
 
 // raw: `count` 13-byte records starting at global rank `first`; prev_kmer = k-mer of rank first-1 (ignored if first == 0)
 __global__ void __launch_bounds__(256) k_parse_ref(const uint8_t *raw, uint64_t first, uint64_t count, uint64_t prev_kmer,
-                                                    RefEntry *out, uint32_t *jg, uint32_t amb_lo, uint32_t n_aux, ParseOut *po)
+                                                    RefEntry *out, uint32_t *jg, uint32_t *jg_lo, uint32_t amb_lo, uint32_t n_aux, ParseOut *po)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t my_max = 0;
@@ -205,10 +205,24 @@ __global__ void __launch_bounds__(256) k_parse_ref(const uint8_t *raw, uint64_t 
 	out[g] = RefEntry{ (uint32_t)kmer, posx };
 	const uint32_t hi = (uint32_t)(kmer >> 32);
 	if (g == 0 || (uint32_t)(pk >> 32) != hi) jg[hi] = (uint32_t)g;
+	atomicAdd(&jg_lo[(uint32_t)kmer], 1u);                          // bucket sizes of the LO32-keyed view
 	if (err) { atomicAdd(&po->errors, 1ull); atomicCAS(&po->first_error_kind, 0u, err); }
 	}
 	my_max = __reduce_max_sync(0xffffffffu, my_max);
 	if ((threadIdx.x & 31) == 0 && my_max) atomicMax(&po->max_pos, my_max);
+}
+
+// LO32-keyed view: one thread per HI32 prefix walks its block and scatters {hi, posx} into the bucket of each entry's LO32.
+// cursor[] holds the bucket starts on entry and the bucket ENDS on exit.
+__global__ void __launch_bounds__(256) k_scatter_by_lo(const RefEntry *ref, const uint32_t *jg, uint32_t *cursor, RefEntry *by_lo)
+{
+	const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lo = jg[h], hi = jg[h + 1];
+	for (uint32_t i = lo; i < hi; i++) {
+		const RefEntry e = ref[i];
+		const uint32_t slot = atomicAdd(&cursor[e.lo], 1u);
+		by_lo[slot] = RefEntry{ (uint32_t)h, e.posx };
+	}
 }
 
 __global__ void __launch_bounds__(256) k_max_u32(const uint32_t *a, uint64_t n, uint32_t *out)
@@ -369,29 +383,37 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 
 	ParseOut *d_po; uint32_t *d_tmp;
 	if ((rc = dev_alloc(c, &d_po, 1, false))) return rc;
-	if ((rc = dev_alloc(c, &d_tmp, (1ull << 32) / JG_TILE + 8, false))) return rc;
+	if ((rc = dev_alloc(c, &d_tmp, (1ull << 32) / SCAN_TILE + 8, false))) return rc;
 	VGB_CUDA(c, cudaMemsetAsync(d_po, 0, sizeof(ParseOut), c->stream));
 
 	// ---- reference dictionary ----
-	RefEntry *d_ref; uint32_t *d_jg; uint32_t *d_aux;
+	RefEntry *d_ref, *d_by_lo; uint32_t *d_jg, *d_jg_lo; uint32_t *d_aux;
 	if ((rc = dev_alloc(c, &d_ref, v->n_ref))) return rc;
+	if ((rc = dev_alloc(c, &d_by_lo, v->n_ref))) return rc;
 	if ((rc = dev_alloc(c, &d_jg, (1ull << 32) + 1))) return rc;
+	if ((rc = dev_alloc(c, &d_jg_lo, (1ull << 32) + 1))) return rc;
+	VGB_CUDA(c, cudaMemsetAsync(d_jg_lo, 0, ((1ull << 32) + 1) * 4, c->stream));
 	if ((rc = dev_alloc(c, &d_aux, v->n_ref_aux * AUX_COLS))) return rc;
 	VGB_CUDA(c, cudaMemsetAsync(d_jg, 0xFF, ((1ull << 32) + 1) * 4, c->stream));
 	if (v->n_ref_aux) VGB_CUDA(c, cudaMemcpyAsync(d_aux, v->ref_aux, v->n_ref_aux * AUX_COLS * 4, cudaMemcpyHostToDevice, c->stream));
 	const uint32_t amb_lo = 0xFFFFFFFFu - (uint32_t)v->n_ref_aux;
 	rc = stream_records(c, v->ref_records, v->n_ref, 13, [&](uint8_t *d_raw, uint64_t first, uint64_t cnt) {
 		const uint64_t prev = first ? rd_kmer(v->ref_records + 13 * (first - 1)) : 0;
-		k_parse_ref<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(d_raw, first, cnt, prev, d_ref, d_jg, amb_lo, (uint32_t)v->n_ref_aux, d_po);
+		k_parse_ref<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(d_raw, first, cnt, prev, d_ref, d_jg, d_jg_lo, amb_lo, (uint32_t)v->n_ref_aux, d_po);
 	});
 	if (rc) return rc;
 	if (v->n_ref_aux) { k_max_u32<<<296, 256, 0, c->stream>>>(d_aux, v->n_ref_aux * AUX_COLS, &d_po->max_pos); c->launches++; }
 	if ((rc = fill_jumpgate(c, d_jg, 32, (uint32_t)v->n_ref, d_tmp))) return rc;
+	// bucket sizes -> bucket starts (in place), then scatter; the cursor array ends up holding bucket ends
+	if ((rc = exclusive_scan_u32(c, d_jg_lo, d_jg_lo, 1ull << 32, d_tmp, nullptr))) return rc;
+	k_scatter_by_lo<<<(unsigned)((1ull << 32) / 256), 256, 0, c->stream>>>(d_ref, d_jg, d_jg_lo, d_by_lo);
+	c->launches++;
 	ParseOut po;
 	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "reference dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	if (po.max_pos >= amb_lo) return set_err(c, VGB_E_INDEX, "reference dictionary: %s", parse_err_text(2));
 	ix.ref = d_ref; ix.n_ref = v->n_ref; ix.ref_jg = d_jg; ix.ref_aux = d_aux; ix.n_ref_aux = (uint32_t)v->n_ref_aux; ix.amb_lo = amb_lo;
+	ix.ref_by_lo = d_by_lo; ix.ref_jg_lo = d_jg_lo;
 
 	// ---- SNP dictionary + static pileup ----
 	// SNP k-mer starts are reference k-mer starts, so sites lie below max_pos + 32 (src/qv.cc:596-603)
