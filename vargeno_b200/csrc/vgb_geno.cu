@@ -13,6 +13,8 @@
 // 32 independent probe chains during the exact and neighbour phases (each probe = jumpgate pair -> short
 // search -> entry, all aligned loads that stay inside one 32 B sector), and 32 pileup positions during the
 // update.  Hit contexts live in shared memory (spill to a per-warp global area only beyond 64 per read).
+#include <cstring>
+
 #include "vgb_internal.h"
 
 namespace vgb {
@@ -45,6 +47,9 @@ struct GenoArgs {
 	DevStats *stats;
 	vgb_read_result *trace;       // nullptr unless VGB_CFG_TRACE
 	Event *spill;                 // [grid warps][EV_CAP - EV_SMEM]
+	const uint32_t *list;         // warp kernel: nullptr = every read of the chunk, else the deferred reads (count in meta[6])
+	uint32_t *defer;              // 8-lane kernel: where deferred read indices go
+	uint32_t debug_stage;         // VGB_DEBUG_STAGE: stop the 8-lane kernel after a phase (bring-up aid), 0 = run everything
 };
 
 struct LaneStats {
@@ -164,17 +169,20 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 	const uint32_t gwarp = blockIdx.x * GW + (threadIdx.x >> 5);
 	Event *spill = a.spill + (uint64_t)gwarp * (EV_CAP - EV_SMEM);
 	const DevIndex &ix = a.ix;
-	const uint32_t n_reads = a.meta[1];
+	// list mode: only the reads the 8-lane kernel deferred (more than 8 k-mers, or more hit contexts than its shared memory holds)
+	const uint32_t n_reads = a.list ? a.meta[6] : a.meta[1];
+	uint32_t *work = a.meta + (a.list ? 7 : 2);
 	LaneStats st;
 	uint32_t w_reads = 0, w_skipped = 0, w_passes = 0, w_placed = 0, w_bad = 0, w_overflow = 0, w_wrap = 0;
 
 	for (;;) {
 		uint32_t r0 = 0;
-		if (lane == 0) r0 = atomicAdd(&a.meta[2], (uint32_t)READ_BATCH);
+		if (lane == 0) r0 = atomicAdd(work, (uint32_t)READ_BATCH);
 		r0 = __shfl_sync(0xffffffffu, r0, 0);
 		if (r0 >= n_reads) break;
 		const uint32_t r1 = min(r0 + READ_BATCH, n_reads);
-		for (uint32_t r = r0; r < r1; r++) {
+		for (uint32_t ri = r0; ri < r1; ri++) {
+			const uint32_t r = a.list ? __ldg(a.list + ri) : ri;
 			// ---- record framing: lines 4r .. 4r+3 (src/qv.cc:760-779) ----
 			uint32_t lsv = lane < 5 ? __ldg(a.line_start + 4ull * r + lane) : 0;
 			const uint32_t id_s = __shfl_sync(0xffffffffu, lsv, 0);
@@ -479,22 +487,37 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 	}
 }
 
+#include "vgb_geno8.inl"
+
 typedef void (*geno_kernel_t)(const GenoArgs);
-static geno_kernel_t g_kernel = nullptr;
+static geno_kernel_t g_warp_kernel = nullptr, g_oct_kernel = nullptr;
+static uint32_t g_oct_grid = 0, g_debug_stage = 0;
 
 int geno_prepare(vgb_ctx *c)
 {
-	// register budget variants of the same kernel: 4 CTAs/SM (64 regs), 6 (40 regs), 8 (32 regs); VGB_GENO_MINB picks one
-	int minb = 4;
+	// VGB_GENO_KERNEL=warp: one warp per read for everything (the first version, kept as the path for deferred reads)
+	// VGB_GENO_MINB / VGB_GENO8_MINB: register budget variants (CTAs per SM the compiler must make room for)
+	int minb = 4, minb8 = 8;     // measured on B200 (profiles/r01_summary.md): the 8-lane kernel is latency bound, 64 warps/SM wins despite spills
 	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
+	if (const char *e = getenv("VGB_GENO8_MINB")) minb8 = atoi(e);
+	const char *kk = getenv("VGB_GENO_KERNEL");
+	const bool warp_only = kk && !strcmp(kk, "warp");
+	if (const char *e = getenv("VGB_DEBUG_STAGE")) g_debug_stage = (uint32_t)atoi(e);
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
-	g_kernel = k;
+	geno_kernel_t k8 = minb8 >= 8 ? k_geno8<8> : (minb8 >= 6 ? k_geno8<6> : (minb8 == 5 ? k_geno8<5> : (minb8 == 3 ? k_geno8<3> : k_geno8<4>)));
+	g_warp_kernel = k;
+	g_oct_kernel = warp_only ? nullptr : k8;
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
 	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
+	const size_t smem8 = sizeof(OctSmem) * GW * 4;
+	VGB_CUDA(c, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k8, GW * 32, smem8));
+	if (occ < 1) occ = 1;
+	g_oct_grid = (uint32_t)(c->sm_count * occ);
 	if (!c->d_spill) {
 		Event *sp = nullptr;
 		int rc = dev_alloc(c, &sp, (uint64_t)c->geno_grid * GW * (EV_CAP - EV_SMEM));
@@ -515,8 +538,19 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.stats = c->d_stats;
 	a.trace = c->d_trace ? c->d_trace + c->trace_n : nullptr;
 	a.spill = (Event *)c->d_spill;
-	g_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
-	c->launches++;
+	a.list = nullptr;
+	a.defer = ck.d_defer;
+	a.debug_stage = g_debug_stage;
+	if (g_oct_kernel) {
+		// main kernel: 8 lanes per read; then the reads it deferred (long reads, context overflow) one warp per read
+		g_oct_kernel<<<g_oct_grid, GW * 32, sizeof(OctSmem) * GW * 4, c->stream>>>(a);
+		a.list = ck.d_defer;
+		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+		c->launches += 2;
+	} else {
+		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+		c->launches++;
+	}
 	VGB_CUDA(c, cudaGetLastError());
 	return VGB_OK;
 }
