@@ -513,7 +513,7 @@ int geno_prepare(vgb_ctx *c)
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
-	const size_t smem8 = sizeof(OctSmem) * GW * 4;
+	const size_t smem8 = sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t);   // hit contexts + one row of counters per warp
 	VGB_CUDA(c, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k8, GW * 32, smem8));
 	if (occ < 1) occ = 1;
@@ -543,7 +543,7 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.debug_stage = g_debug_stage;
 	if (g_oct_kernel) {
 		// main kernel: 8 lanes per read; then the reads it deferred (long reads, context overflow) one warp per read
-		g_oct_kernel<<<g_oct_grid, GW * 32, sizeof(OctSmem) * GW * 4, c->stream>>>(a);
+		g_oct_kernel<<<g_oct_grid, GW * 32, sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t), c->stream>>>(a);
 		a.list = ck.d_defer;
 		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches += 2;

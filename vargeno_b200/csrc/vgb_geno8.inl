@@ -135,8 +135,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 #define OSHFL(v, src) __shfl_sync(FULL, (v), ob | (src))
 #define OBALLOT(p) ((__ballot_sync(FULL, (p)) >> ob) & 0xFFu)
 
-	LaneStats st;
-	uint32_t w_reads = 0, w_skipped = 0, w_passes = 0, w_placed = 0, w_bad = 0, w_wrap = 0;
+	// statistics live in shared memory (one row of 16 counters per warp), not in registers: the kernel runs at 32
+	// registers per thread and every counter kept in a register is a spill somewhere else
+	uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * 4) + (threadIdx.x >> 5) * 16;
+	enum { A_EXACT, A_NBRQ, A_SCAN, A_BF, A_LOWQ, A_EVENTS, A_INCR, A_BIG, A_READS, A_SKIPPED, A_PASSES, A_PLACED, A_BAD, A_WRAP };
+	if (lane < 16) acc[lane] = 0;
+	__syncwarp();
 
 	for (;;) {
 		uint32_t r0 = 0;
@@ -360,25 +364,34 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (a.debug_stage == 4) { done = true; continue; }
 			// ---- pileup update: every recorded context at the winning position (src/qv.cc:1382-1502) ----
 			if (vrun && process) {
+				const uint64_t n_blk = ix.pile_len >> 6;
 				for (uint32_t e = 0; e < E; e++) {
 					const Event *p = &os->ev[e];
 					if (p->X != target) continue;
 					const uint32_t mod = p->meta & 0xFF;
 					const uint64_t kmer_e = p->kmer;
-					const uint32_t kpos = p->kpos;
-#pragma unroll
-					for (uint32_t c = 0; c < 4; c++) {
-						const uint32_t b = ol + 8 * c;
-						const uint64_t pos = (uint64_t)kpos + b;
-						if (b == mod || pos >= ix.pile_len) continue;
-						const uint4 blk = __ldg(reinterpret_cast<const uint4 *>(ix.pile + (pos >> 6)));
-						const uint64_t bits = ((uint64_t)blk.y << 32) | blk.x;
-						const uint32_t off = pos & 63;
-						if (!((bits >> off) & 1ull)) continue;
-						const uint32_t sid = blk.z + __popcll(bits & ((1ull << off) - 1));
+					const uint64_t kpos = p->kpos;
+					// the 32-position window [kpos, kpos+32) lies in one or two 64-position blocks; every lane of the octet
+					// loads the same 16-byte block records (one transaction), then looks only at its own four positions
+					const uint64_t bA = kpos >> 6, bB = (kpos + 31) >> 6;
+					uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
+					if (bA < n_blk) ka = __ldg(reinterpret_cast<const uint4 *>(ix.pile + bA));
+					if (bB != bA && bB < n_blk) kb = __ldg(reinterpret_cast<const uint4 *>(ix.pile + bB));
+					const uint64_t bitsA = ((uint64_t)ka.y << 32) | ka.x, bitsB = ((uint64_t)kb.y << 32) | kb.x;
+					const uint32_t sh = (uint32_t)(kpos & 63);
+					uint32_t win = (uint32_t)(bitsA >> sh);
+					if (sh > 32) win |= (uint32_t)(bitsB << (64 - sh));
+					uint32_t mineb = win & (0x01010101u << ol);        // my positions: ol, ol+8, ol+16, ol+24
+					if (mod < 32) mineb &= ~(1u << mod);               // the substituted base does not count (:1391)
+					while (mineb) {
+						const uint32_t b = __ffs(mineb) - 1;
+						mineb &= mineb - 1;
+						const uint32_t off = sh + b;                    // bit index relative to block A
+						const uint32_t sid = off < 64 ? ka.z + __popcll(bitsA & ((1ull << off) - 1))
+						                              : kb.z + __popcll(bitsB & ((1ull << (off - 64)) - 1));
 						const uint32_t code = __ldg(ix.site_code + sid);
 						const uint32_t rbase = code & 3, abase = code >> 2;
-						if (rbase == abase) continue;              // p->ref != p->alt (:1404)
+						if (rbase == abase) continue;                  // p->ref != p->alt (:1404)
 						const uint32_t base = (uint32_t)(kmer_e >> (2 * b)) & 3u;
 						if (base == rbase) { atomicAdd(ix.cnt + 2ull * sid, 1u); rs.incr_big += 1; }
 						else if (base == abase) { atomicAdd(ix.cnt + 2ull * sid + 1, 1u); rs.incr_big += 1; }
@@ -391,22 +404,26 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 		// ---- per-read bookkeeping (lane 0 of the octet speaks for the read) ----
 		if (have && !defer) {
-			st.exact += rs.exact_nbrq & 0xFFFF; st.nbrq += rs.exact_nbrq >> 16;
-			st.scan += rs.scan_bf & 0xFFFF; st.bf += rs.scan_bf >> 16;
-			st.lowq += rs.lowq_events & 0xFFFF; st.events += rs.lowq_events >> 16;
-			st.incr += rs.incr_big & 0xFFFF; st.big += rs.incr_big >> 16;
+			if (rs.exact_nbrq & 0xFFFF) atomicAdd(&acc[A_EXACT], rs.exact_nbrq & 0xFFFF);
+			if (rs.exact_nbrq >> 16) atomicAdd(&acc[A_NBRQ], rs.exact_nbrq >> 16);
+			if (rs.scan_bf & 0xFFFF) atomicAdd(&acc[A_SCAN], rs.scan_bf & 0xFFFF);
+			if (rs.scan_bf >> 16) atomicAdd(&acc[A_BF], rs.scan_bf >> 16);
+			if (rs.lowq_events & 0xFFFF) atomicAdd(&acc[A_LOWQ], rs.lowq_events & 0xFFFF);
+			if (rs.lowq_events >> 16) atomicAdd(&acc[A_EVENTS], rs.lowq_events >> 16);
+			if (rs.incr_big & 0xFFFF) atomicAdd(&acc[A_INCR], rs.incr_big & 0xFFFF);
+			if (rs.incr_big >> 16) atomicAdd(&acc[A_BIG], rs.incr_big >> 16);
 		}
 		if (have && ol == 0) {
 			if (defer) {
 				a.defer[atomicAdd(&a.meta[6], 1u)] = r;
 			} else {
-				w_reads++;
-				w_passes += passes;
-				if (bad) { w_bad++; atomicOr(&a.meta[3], 2u); }
-				else if (skipped) w_skipped++;
+				atomicAdd(&acc[A_READS], 1u);
+				if (passes) atomicAdd(&acc[A_PASSES], passes);
+				if (bad) { atomicAdd(&acc[A_BAD], 1u); atomicOr(&a.meta[3], 2u); }
+				else if (skipped) atomicAdd(&acc[A_SKIPPED], 1u);
 				else {
-					if (process) w_placed++;
-					if (best_freq > 255) w_wrap++;
+					if (process) atomicAdd(&acc[A_PLACED], 1u);
+					if (best_freq > 255) atomicAdd(&acc[A_WRAP], 1u);
 				}
 				if (a.trace) {
 					vgb_read_result res;
@@ -424,25 +441,16 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 #undef OSHFL
 #undef OBALLOT
 
-	unsigned long long v[8] = { st.exact, st.nbrq, st.scan, st.bf, st.lowq, st.events, st.incr, st.big };
-#pragma unroll
-	for (int k = 0; k < 8; k++) {
-#pragma unroll
-		for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
-	}
-	unsigned long long u[6] = { w_reads, w_skipped, w_passes, w_placed, w_bad, w_wrap };
-#pragma unroll
-	for (int k = 0; k < 6; k++) {
-#pragma unroll
-		for (int o = 16; o; o >>= 1) u[k] += __shfl_xor_sync(FULL, u[k], o);
-	}
+	__syncwarp();
 	if (lane == 0) {
 		DevStats *s = a.stats;
-		atomicAdd(&s->reads, u[0]); atomicAdd(&s->skipped_n, u[1]); atomicAdd(&s->passes, u[2]); atomicAdd(&s->placed, u[3]);
-		atomicAdd(&s->exact_lookups, v[0]); atomicAdd(&s->nbr_query_lookups, v[1]); atomicAdd(&s->nbr_scan_reads, v[2]);
-		atomicAdd(&s->bf_probes, v[3]); atomicAdd(&s->lowq_kmers, v[4]); atomicAdd(&s->events, v[5]);
-		atomicAdd(&s->pileup_incr, v[6]); atomicAdd(&s->big_kmers, v[7]);
-		if (u[4]) atomicAdd(&s->bad_records, u[4]);
-		if (u[5]) atomicAdd(&s->freq_wrap_reads, u[5]);
+		atomicAdd(&s->reads, (unsigned long long)acc[A_READS]); atomicAdd(&s->skipped_n, (unsigned long long)acc[A_SKIPPED]);
+		atomicAdd(&s->passes, (unsigned long long)acc[A_PASSES]); atomicAdd(&s->placed, (unsigned long long)acc[A_PLACED]);
+		atomicAdd(&s->exact_lookups, (unsigned long long)acc[A_EXACT]); atomicAdd(&s->nbr_query_lookups, (unsigned long long)acc[A_NBRQ]);
+		atomicAdd(&s->nbr_scan_reads, (unsigned long long)acc[A_SCAN]); atomicAdd(&s->bf_probes, (unsigned long long)acc[A_BF]);
+		atomicAdd(&s->lowq_kmers, (unsigned long long)acc[A_LOWQ]); atomicAdd(&s->events, (unsigned long long)acc[A_EVENTS]);
+		atomicAdd(&s->pileup_incr, (unsigned long long)acc[A_INCR]); atomicAdd(&s->big_kmers, (unsigned long long)acc[A_BIG]);
+		if (acc[A_BAD]) atomicAdd(&s->bad_records, (unsigned long long)acc[A_BAD]);
+		if (acc[A_WRAP]) atomicAdd(&s->freq_wrap_reads, (unsigned long long)acc[A_WRAP]);
 	}
 }
