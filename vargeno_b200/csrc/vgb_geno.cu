@@ -497,7 +497,7 @@ int geno_prepare(vgb_ctx *c)
 {
 	// VGB_GENO_KERNEL=warp: one warp per read for everything (the first version, kept as the path for deferred reads)
 	// VGB_GENO_MINB / VGB_GENO8_MINB: register budget variants (CTAs per SM the compiler must make room for)
-	int minb = 4, minb8 = 8;     // measured on B200 (profiles/r01_summary.md): the 8-lane kernel is latency bound, 64 warps/SM wins despite spills
+	int minb = 4, minb8 = 6;     // measured on B200 (profiles/r01_summary.md): 40 registers / 48 warps per SM is the sweet spot (8 CTAs/SM spills too much)
 	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
 	if (const char *e = getenv("VGB_GENO8_MINB")) minb8 = atoi(e);
 	const char *kk = getenv("VGB_GENO_KERNEL");

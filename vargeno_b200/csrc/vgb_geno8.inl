@@ -13,22 +13,25 @@
 
 constexpr int OCT_EV = 24;            // hit contexts per read kept in shared memory
 
+// per-read statistics are kept in the octet's shared memory (committed only when the read is finished here, not when it
+// is deferred): at 32 registers per thread every counter held in a register would be a spill
+enum { S_EXACT, S_NBRQ, S_SCAN, S_BF, S_LOWQ, S_EVENTS, S_INCR, S_BIG };
+
 struct OctSmem {
 	Event ev[OCT_EV];
+	uint32_t st[8];
 	uint32_t ev_count;
+	// vote result of the read's final pass, written by the octet's lane 0 (kept here, not in registers, until bookkeeping)
+	uint32_t res_flags, res_target, res_freq, res_nref, res_nsnp, res_passes;
 	uint32_t pad;
+	uint64_t res_dg;
 };
-
-// per-read statistics, packed 2 x 16 bit, committed only when the read is finished here (not when it is deferred)
-struct ReadStats {
-	uint32_t exact_nbrq = 0, scan_bf = 0, lowq_events = 0, incr_big = 0;
-};
+typedef OctSmem ReadStats;     // the emit / event helpers count through the same pointer
 
 __device__ __forceinline__ void emit8(OctSmem *os, uint64_t kmer, uint32_t pos, uint32_t offset, uint32_t mod, uint32_t kidx,
-                                      uint32_t list, ReadStats &rs)
+                                      uint32_t list, ReadStats *rs)
 {
 	const uint32_t i = atomicAdd(&os->ev_count, 1u);
-	rs.lowq_events += 1u << 16;
 	if (i >= OCT_EV) return;                                  // overflow: the read is deferred after this pass
 	Event e;
 	e.kmer = kmer; e.X = pos - offset; e.kpos = pos; e.meta = mod | (kidx << 8) | (list << 16); e.pad = 0;
@@ -36,7 +39,7 @@ __device__ __forceinline__ void emit8(OctSmem *os, uint64_t kmer, uint32_t pos, 
 }
 
 __device__ __forceinline__ void exact_ref_events8(const DevIndex &ix, OctSmem *os, uint64_t kmer, uint32_t posx, uint32_t offset,
-                                                  uint32_t kidx, ReadStats &rs)
+                                                  uint32_t kidx, ReadStats *rs)
 {
 	if (posx == POS_AMBIGUOUS) return;
 	if (posx < ix.amb_lo) { emit8(os, kmer, posx, offset, NO_MOD, kidx, 0, rs); return; }
@@ -48,7 +51,7 @@ __device__ __forceinline__ void exact_ref_events8(const DevIndex &ix, OctSmem *o
 	}
 }
 __device__ __forceinline__ void exact_snp_events8(const DevIndex &ix, OctSmem *os, uint64_t kmer, const SnpEntry &e, uint32_t offset,
-                                                  uint32_t kidx, ReadStats &rs)
+                                                  uint32_t kidx, ReadStats *rs)
 {
 	if (e.pos == POS_AMBIGUOUS) return;
 	if (snp_flag_of(e) == 0) { emit8(os, kmer, e.pos, offset, NO_MOD, kidx, 1, rs); return; }
@@ -60,7 +63,7 @@ __device__ __forceinline__ void exact_snp_events8(const DevIndex &ix, OctSmem *o
 	}
 }
 __device__ __forceinline__ void nbr_ref_events8(const DevIndex &ix, OctSmem *os, uint64_t nb, uint32_t posx, uint32_t d, uint32_t offset,
-                                                uint32_t kidx, ReadStats &rs)
+                                                uint32_t kidx, ReadStats *rs)
 {
 	if (posx == POS_AMBIGUOUS) return;
 	if (posx < ix.amb_lo) {
@@ -75,7 +78,7 @@ __device__ __forceinline__ void nbr_ref_events8(const DevIndex &ix, OctSmem *os,
 	}
 }
 __device__ __forceinline__ void nbr_snp_events8(const DevIndex &ix, OctSmem *os, uint64_t nb, const SnpEntry &e, uint32_t d, uint32_t offset,
-                                                uint32_t kidx, ReadStats &rs)
+                                                uint32_t kidx, ReadStats *rs)
 {
 	if (e.pos == POS_AMBIGUOUS) return;
 	if (snp_flag_of(e) == 0) {
@@ -182,10 +185,11 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		if (active && ol < K) lowq = ((int)(signed char)__ldg(a.text + qual_s + ol) - QUALITY_SCORE) < 0;
 
 		if (a.debug_stage == 1) continue;
-		ReadStats rs;
-		bool process = false, has_best = false, ambiguous = false, done = !active;
-		uint32_t target = 0, best_freq = 0, passes = 0, E = 0, nref = 0, nsnp = 0;
-		uint64_t dg = 0;
+		os->st[ol] = 0;
+		ReadStats *rs = os;
+		bool done = !active;
+		if (ol == 0) { os->res_flags = 0; os->res_target = 0; os->res_freq = 0; os->res_nref = 0; os->res_nsnp = 0; os->res_passes = 0; os->res_dg = 0; }
+		uint32_t E = 0;
 
 		for (uint32_t pass = 0; pass < 2; pass++) {
 			const bool run = active && !done;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				kmer = ol < K ? revcomp64(o) : 0;
 			}
 			if (run && ol == 0) os->ev_count = 0;
-			if (run) passes = pass + 1;
+			if (run && ol == 0) os->res_passes = pass + 1;
 			__syncwarp();
 
 			// ---- level 1: everything that depends only on the k-mer is put in flight together ----
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (mine) {
 				ref_block(ix, kmer, rlo, rhi);
 				snp_block(ix, kmer, slo, shi);
-				rs.exact_nbrq += 2;
+				atomicAdd(&os->st[S_EXACT], 2u);
 			}
 			if (gates) {
 				bfr_bit = hash32((uint32_t)kmer);
@@ -216,8 +220,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				if ((bfr_bit >> 5) < ix.ref_bf_nw32) bfr_w = __ldg(ix.ref_bf + (bfr_bit >> 5));
 				if ((bfs_bit >> 5) < ix.snp_bf_nw32) bfs_w = __ldg(ix.snp_bf + (bfs_bit >> 5));
 				ref_lo_bucket(ix, (uint32_t)kmer, bs, be);     // speculative: used only if the ref Bloom gate is open
-				rs.scan_bf += 2u << 16;
-				rs.lowq_events += 1;
+				atomicAdd(&os->st[S_BF], 2u);
+				atomicAdd(&os->st[S_LOWQ], 1u);
 			}
 			// ---- level 2: exact entries (src/qv.cc:840-937) ----
 			if (mine) {
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (!rb) { bs = 0; be = 0; }
 			const uint32_t rB = rhi - rlo, sB = shi - slo;
 			const bool big = rB >= BLOCK_SIZE_THRESHOLD;       // src/qv.cc:843,962
-			if (gates) { if (rb) rs.exact_nbrq += 48u << 16; if (big) rs.incr_big += 1u << 16; }
+			if (gates) { if (rb) atomicAdd(&os->st[S_NBRQ], 48u); if (big) atomicAdd(&os->st[S_BIG], 1u); }
 
 			if (a.debug_stage == 2) { done = true; continue; }
 			// ---- Hamming-1 neighbours: the octet works through its low-quality k-mers one at a time ----
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						const uint32_t u = t - e2, d = u / 3;
 						const uint64_t nb = substitute(km, d, u % 3);
 						uint32_t posx;
-						rs.exact_nbrq += 1u << 16;
+						atomicAdd(&os->st[S_NBRQ], 1u);
 						if (ref_query(ix, nb, posx) >= 0) nbr_ref_events8(ix, os, nb, posx, d, offset, i, rs);
 					} else if (t < e2 || (t >= e3 && k_big)) {
 						uint32_t u, d;
@@ -271,12 +275,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						else { u = t - e3; d = u / 3; }
 						const uint64_t nb = substitute(km, d, u % 3);
 						SnpEntry e;
-						rs.exact_nbrq += 1u << 16;
+						atomicAdd(&os->st[S_NBRQ], 1u);
 						if (snp_query(ix, nb, e) >= 0) nbr_snp_events8(ix, os, nb, e, d, offset, i, rs);
 					} else if (t < e3) {                              // ref strided scan step (F13)
 						const uint32_t s = t - e2;
 						const uint64_t ex = (uint64_t)k_rlo + (uint64_t)REF_STRIDE * s;
-						rs.scan_bf += 1;
+						atomicAdd(&os->st[S_SCAN], 1u);
 						if (ex < ix.n_ref) {
 							const uint32_t entry_lo = __ldg(&ix.ref[ex].lo);
 							const int d = one_base_slot((uint64_t)((uint32_t)km ^ entry_lo));
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					} else {                                          // snp strided scan step (F13)
 						const uint32_t s = t - e3;
 						const uint64_t ex = (uint64_t)k_slo + (uint64_t)SNP_STRIDE * s;
-						rs.scan_bf += 1;
+						atomicAdd(&os->st[S_SCAN], 1u);
 						if (ex < ix.n_snp) {
 							const uint64_t entry_lo = __ldg(&ix.snp[ex].key) & 0xFFFFFFFFFFull;
 							const int d = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 			// ---- vote (src/qv.cc:132-178, order-independent form) ----
 			E = run ? os->ev_count : 0;
+			if (run && ol == 0) os->st[S_EVENTS] += E;
 			if (E > OCT_EV) { defer = true; done = true; E = 0; }   // too many contexts for shared memory: redo in k_geno
 			const bool vrun = run && !defer;
 			for (uint32_t e = ol; e < E; e += 8) {
@@ -352,13 +357,14 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				t_nsnp += __shfl_xor_sync(FULL, t_nsnp, o);
 				t_dg += __shfl_xor_sync(FULL, t_dg, o);
 			}
-			if (vrun) {
-				nref = t_nref; nsnp = t_nsnp; dg = t_dg;
-				has_best = maxf > 0;
-				ambiguous = has_best && xmin != xmax;
-				process = has_best && !ambiguous;              // freq > 1 is implied by two distinct k-mer positions (:1375)
-				target = xmin;
-				best_freq = maxf;
+			const bool has_best = maxf > 0;
+			const bool ambiguous = has_best && xmin != xmax;
+			const bool process = has_best && !ambiguous;       // freq > 1 is implied by two distinct k-mer positions (:1375)
+			const uint32_t target = xmin;
+			if (vrun && ol == 0) {
+				os->res_nref = t_nref; os->res_nsnp = t_nsnp; os->res_dg = t_dg; os->res_target = target; os->res_freq = maxf;
+				os->res_flags = (pass ? VGB_RF_REVCOMPL : 0) | (process ? VGB_RF_PROCESS : 0) | (ambiguous ? VGB_RF_AMBIGUOUS : 0) |
+				                (has_best ? VGB_RF_HASBEST : 0);
 			}
 
 			if (a.debug_stage == 4) { done = true; continue; }
@@ -393,8 +399,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						const uint32_t rbase = code & 3, abase = code >> 2;
 						if (rbase == abase) continue;                  // p->ref != p->alt (:1404)
 						const uint32_t base = (uint32_t)(kmer_e >> (2 * b)) & 3u;
-						if (base == rbase) { atomicAdd(ix.cnt + 2ull * sid, 1u); rs.incr_big += 1; }
-						else if (base == abase) { atomicAdd(ix.cnt + 2ull * sid + 1, 1u); rs.incr_big += 1; }
+						if (base == rbase) { atomicAdd(ix.cnt + 2ull * sid, 1u); atomicAdd(&os->st[S_INCR], 1u); }
+						else if (base == abase) { atomicAdd(ix.cnt + 2ull * sid + 1, 1u); atomicAdd(&os->st[S_INCR], 1u); }
 					}
 				}
 			}
@@ -404,34 +410,27 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 		// ---- per-read bookkeeping (lane 0 of the octet speaks for the read) ----
 		if (have && !defer) {
-			if (rs.exact_nbrq & 0xFFFF) atomicAdd(&acc[A_EXACT], rs.exact_nbrq & 0xFFFF);
-			if (rs.exact_nbrq >> 16) atomicAdd(&acc[A_NBRQ], rs.exact_nbrq >> 16);
-			if (rs.scan_bf & 0xFFFF) atomicAdd(&acc[A_SCAN], rs.scan_bf & 0xFFFF);
-			if (rs.scan_bf >> 16) atomicAdd(&acc[A_BF], rs.scan_bf >> 16);
-			if (rs.lowq_events & 0xFFFF) atomicAdd(&acc[A_LOWQ], rs.lowq_events & 0xFFFF);
-			if (rs.lowq_events >> 16) atomicAdd(&acc[A_EVENTS], rs.lowq_events >> 16);
-			if (rs.incr_big & 0xFFFF) atomicAdd(&acc[A_INCR], rs.incr_big & 0xFFFF);
-			if (rs.incr_big >> 16) atomicAdd(&acc[A_BIG], rs.incr_big >> 16);
+			const uint32_t v = os->st[ol];                     // lane ol commits counter ol (S_* and A_* share the first 8 slots)
+			if (v) atomicAdd(&acc[ol], v);
 		}
 		if (have && ol == 0) {
 			if (defer) {
 				a.defer[atomicAdd(&a.meta[6], 1u)] = r;
 			} else {
 				atomicAdd(&acc[A_READS], 1u);
+				const uint32_t passes = os->res_passes, flags = os->res_flags, best_freq = os->res_freq;
 				if (passes) atomicAdd(&acc[A_PASSES], passes);
 				if (bad) { atomicAdd(&acc[A_BAD], 1u); atomicOr(&a.meta[3], 2u); }
 				else if (skipped) atomicAdd(&acc[A_SKIPPED], 1u);
 				else {
-					if (process) atomicAdd(&acc[A_PLACED], 1u);
+					if (flags & VGB_RF_PROCESS) atomicAdd(&acc[A_PLACED], 1u);
 					if (best_freq > 255) atomicAdd(&acc[A_WRAP], 1u);
 				}
 				if (a.trace) {
 					vgb_read_result res;
-					res.flags = (bad || skipped) ? VGB_RF_SKIPPED
-					            : ((passes == 2 ? VGB_RF_REVCOMPL : 0) | (process ? VGB_RF_PROCESS : 0) | (ambiguous ? VGB_RF_AMBIGUOUS : 0) |
-					               (has_best ? VGB_RF_HASBEST : 0));
-					res.target = target; res.freq = (uint16_t)(best_freq & 0xFF);
-					res.n_ref = (uint16_t)nref; res.n_snp = (uint16_t)nsnp; res.passes = (uint16_t)passes; res.ctx_hash = dg;
+					res.flags = (bad || skipped) ? VGB_RF_SKIPPED : flags;
+					res.target = os->res_target; res.freq = (uint16_t)(best_freq & 0xFF);
+					res.n_ref = (uint16_t)os->res_nref; res.n_snp = (uint16_t)os->res_nsnp; res.passes = (uint16_t)passes; res.ctx_hash = os->res_dg;
 					if (bad || skipped) { res.target = 0; res.freq = 0; res.n_ref = 0; res.n_snp = 0; res.passes = 0; res.ctx_hash = 0; }
 					a.trace[r] = res;
 				}
