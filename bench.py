@@ -228,7 +228,7 @@ def run_ours(args):
             "lookups_per_read": d_lookups / max(1, st1["reads"] - st0["reads"]),
             "placed_fraction": (st1["placed"] - st0["placed"]) / max(1, st1["reads"] - st0["reads"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_geno", "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": d_ms_geno / K,
+                         "kernel": "k_geno8 (+ list-mode k_geno for deferred reads)", "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": d_ms_geno / K,
                          "peak_source": peak_src, "note": "32 B (one DRAM sector) per dictionary lookup, SURVEY.md 8(d)",
                          "random_sector_peak_gbs": rs, "frac_of_random_sector_peak": (achieved / rs) if rs else None},
             "kernel_ms_per_step": {"k_geno": d_ms_geno / K, "fastq_framing": d_ms_parse / K},
