@@ -194,6 +194,59 @@ def test_format_violations_are_loud(cache):
         assert st["reads"] == 2 and st["skipped_n"] == 1
 
 
+def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
+    """Reads of 288+ bases (more than 8 k-mers) and reads with more hit contexts than the 8-lane kernel keeps in shared
+    memory are handed to the warp-per-read kernel; results must not depend on which kernel handled a read."""
+    from vargeno_b200.geno import Genotyper
+    from vargeno_b200.tools import synth
+    import datasets
+    ix = cache.index("advB")
+    # rebuild the advB genome/haplotypes (pure function of its seeds) and draw long reads from it
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        ds = datasets.make_adv_b(d)
+        names, seqs = [], []
+        from vargeno_b200.tools import index_builder as ib
+        names, seqs = ib.read_fasta_raw(ds.fasta)
+    g0 = synth.Genome(names, seqs)
+    haps = (g0.concat(), g0.concat())
+    parts, first = [], 0
+    for L, n in ((288, 600), (320, 600), (650, 400), (1000, 300), (150, 800), (100, 400)):
+        parts.append(synth.simulate_reads(g0, haps, n, L, seed=77 + L, sub_rate=0.01, lowq_prob=0.7, lowq_chars=31, first_id=first))
+        first += n
+    fq = np.concatenate(parts)
+    o = orc.Oracle(ix)
+    want = o.process_fastq(fq)
+    with Genotyper(device=0, trace=True, max_chunk_bytes=1 << 20) as g:
+        g.upload_index(ix)
+        g.submit(fq)
+        g.sync()
+        got = g.read_results()
+        r, a = g.pileup()
+        st = g.stats()
+    for f in ("flags", "freq", "n_ref", "n_snp", "passes", "ctx_hash"):
+        bad = np.flatnonzero(got[f] != want[f])
+        assert bad.size == 0, "%s differs for %d reads, first %s" % (f, bad.size, bad[:5])
+    sites = o.sites()
+    assert np.array_equal(r, sites["ref_cnt"]) and np.array_equal(a, sites["alt_cnt"])
+    ost = o.stats()
+    for k in ("reads", "passes", "placed", "exact_lookups", "nbr_query_lookups", "nbr_scan_reads", "events", "pileup_incr", "big_kmers"):
+        assert st[k] == ost[k], k
+    assert int(want["n_ref"].max()) + int(want["n_snp"].max()) > 24, "the set should contain reads beyond the shared-memory context budget"
+    o.close()
+    # the warp-per-read kernel alone gives the same answer
+    os.environ["VGB_GENO_KERNEL"] = "warp"
+    try:
+        with Genotyper(device=0, trace=True, max_chunk_bytes=1 << 20) as g:
+            g.upload_index(ix)
+            g.submit(fq)
+            g.sync()
+            got2 = g.read_results()
+    finally:
+        os.environ.pop("VGB_GENO_KERNEL", None)
+    assert np.array_equal(got, got2)
+
+
 def test_device_read_simulator_matches_numpy(cache):
     """vgb_synth_reads_device is the bench's input generator; it must emit the bytes tools/synth.simulate_reads does."""
     from vargeno_b200.geno import Genotyper
