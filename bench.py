@@ -85,6 +85,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(device):
+    """Run this rank on the CPUs NVML names as closest to its GPU, so that the pinned FASTQ buffers (first touched by this
+    process) sit in host memory of the same NUMA node as the GPU's PCIe root.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d" % (min(cpus), max(cpus)) if len(cpus) > 1 else "cpu %d" % cpus[0]
+    except Exception as e:     # best effort: the number is still valid without it, only possibly slower
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -98,6 +117,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_near_gpu(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -190,9 +210,12 @@ def run_ours(args):
     for i in range(W, nb):
         g.submit_chunk(host[i * batch_bytes:(i + 1) * batch_bytes], first + i * B)
     g.sync()
+    t_reads = time.perf_counter() - t0
     if world > 1:
         g.allreduce()
+    t_reduce = time.perf_counter() - t0 - t_reads
     gt, conf = g.call()                     # device -> host read of the job's result (GT + confidence per SNP site)
+    t_call = time.perf_counter() - t0 - t_reads - t_reduce
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = K * reads_step / dt_e2e
@@ -234,9 +257,11 @@ def run_ours(args):
             "kernel_ms_per_step": {"k_geno": d_ms_geno / K, "fastq_framing": d_ms_parse / K},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": batch_bytes * world,
-                    "d2h_bytes_per_step": int(n_sites * 9 * world / K), "ms_per_step": dt_e2e / K * 1e3},
+                    "d2h_bytes_per_step": int(n_sites * 9 * world / K), "ms_per_step": dt_e2e / K * 1e3,
+                    "rank0_ms": {"submit_and_sync": t_reads * 1e3, "allreduce": t_reduce * 1e3, "call_d2h": t_call * 1e3}},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "host_binding": numa,
             "setup_s": setup_s,
         }
         print(json.dumps(out), flush=True)

@@ -51,16 +51,18 @@ int call_sites(vgb_ctx *c, uint8_t *gtype, double *conf, uint64_t n_sites)
 	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
 	if (n_sites != c->ix.n_sites) return set_err(c, VGB_E_ARG, "n_sites is %llu, index has %llu", (unsigned long long)n_sites, (unsigned long long)c->ix.n_sites);
 	if (n_sites == 0) return VGB_OK;
-	uint8_t *d_g; double *d_c;
 	int rc;
-	if ((rc = dev_alloc(c, &d_g, n_sites, false))) return rc;
-	if ((rc = dev_alloc(c, &d_c, n_sites, false))) { cudaFree(d_g); return rc; }
+	// output staging is allocated once per context: cudaMalloc / cudaFree in the call path would serialise with every
+	// other context of the process (and of the node) on the driver lock
+	if (!c->d_call_gt && (rc = dev_alloc(c, &c->d_call_gt, n_sites))) return rc;
+	if (!c->d_call_conf && (rc = dev_alloc(c, &c->d_call_conf, n_sites))) return rc;
+	uint8_t *d_g = c->d_call_gt;
+	double *d_c = c->d_call_conf;
 	k_call<<<(unsigned)((n_sites + 255) / 256), 256, 0, c->stream>>>(c->ix.cnt, c->ix.site_code, c->d_site_rf, c->d_site_af, n_sites, c->d_tables, d_g, d_c);
 	c->launches++;
 	cudaError_t e = cudaMemcpyAsync(gtype, d_g, n_sites, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(conf, d_c, n_sites * 8, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_g); cudaFree(d_c);
 	if (e != cudaSuccess) return set_err(c, VGB_E_CUDA, "caller kernel failed: %s", cudaGetErrorString(e));
 	return VGB_OK;
 }
@@ -70,16 +72,15 @@ int fetch_pileup(vgb_ctx *c, uint32_t *ref_cnt, uint32_t *alt_cnt, uint64_t n_si
 	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
 	if (n_sites != c->ix.n_sites) return set_err(c, VGB_E_ARG, "n_sites is %llu, index has %llu", (unsigned long long)n_sites, (unsigned long long)c->ix.n_sites);
 	if (n_sites == 0) return VGB_OK;
-	uint32_t *d_r, *d_a;
 	int rc;
-	if ((rc = dev_alloc(c, &d_r, n_sites, false))) return rc;
-	if ((rc = dev_alloc(c, &d_a, n_sites, false))) { cudaFree(d_r); return rc; }
+	if (!c->d_fetch_ref && (rc = dev_alloc(c, &c->d_fetch_ref, n_sites))) return rc;
+	if (!c->d_fetch_alt && (rc = dev_alloc(c, &c->d_fetch_alt, n_sites))) return rc;
+	uint32_t *d_r = c->d_fetch_ref, *d_a = c->d_fetch_alt;
 	k_split_counts<<<(unsigned)((n_sites + 255) / 256), 256, 0, c->stream>>>(c->ix.cnt, n_sites, d_r, d_a);
 	c->launches++;
 	cudaError_t e = cudaMemcpyAsync(ref_cnt, d_r, n_sites * 4, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(alt_cnt, d_a, n_sites * 4, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_r); cudaFree(d_a);
 	if (e != cudaSuccess) return set_err(c, VGB_E_CUDA, "pileup fetch failed: %s", cudaGetErrorString(e));
 	return VGB_OK;
 }

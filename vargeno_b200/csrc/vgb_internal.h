@@ -55,6 +55,9 @@ struct vgb_ctx {
 	uint64_t trace_cap = 0, trace_n = 0;
 	uint32_t sticky_format = 0;      // format error bits seen since the last reset
 	void *d_spill = nullptr;         // per-warp overflow area for hit contexts
+	uint8_t *d_call_gt = nullptr;    // per-site output staging of vgb_call / vgb_fetch_pileup (allocated once, at first use)
+	double *d_call_conf = nullptr;
+	uint32_t *d_fetch_ref = nullptr, *d_fetch_alt = nullptr;
 	uint32_t geno_grid = 0;
 
 	// host-side statistics
