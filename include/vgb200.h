@@ -162,6 +162,22 @@ int  vgb_synth_reads_device(vgb_ctx *ctx, const uint8_t *hap0, const uint8_t *ha
                             const uint64_t *contig_starts, const uint64_t *contig_lens, uint32_t n_contigs,
                             uint64_t n_reads, uint32_t read_len, uint64_t seed, uint64_t first_id, uint32_t id_width,
                             double sub_rate, double lowq_prob, uint32_t lowq_chars, char *device_out, uint64_t out_cap);
+/* ---- index tooling on the device ("next" rows; not part of the drop-in surface) ----
+ * vgb_build_index_device: the records `vargeno index` would write (src/dictgen.c:63-275, src/generate_bf.cc:107-154,
+ * 238-262), built in HBM from an upper-case ACGTN genome (device pointer, contigs concatenated) and the SNP lines that
+ * survive the VCF filters (host arrays, file order; positions are 0-based in the concatenation; code = ref | alt << 2).
+ * `out` receives DEVICE pointers in the on-disk record layouts; pass it to vgb_index_upload_device, copy it back with
+ * vgb_memcpy_d2h to write the files, release it with vgb_free_index_device. */
+int  vgb_build_index_device(vgb_ctx *ctx, const uint8_t *device_genome, uint64_t genome_len,
+                            const uint64_t *contig_starts, const uint64_t *contig_lens, uint32_t n_contigs,
+                            const uint32_t *snp_pos0, const uint8_t *snp_code, const uint8_t *snp_ref_freq, const uint8_t *snp_alt_freq,
+                            uint64_t n_snp_lines, const uint32_t *bf_pos0, uint64_t n_bf_lines, vgb_index_view *out);
+void vgb_free_index_device(vgb_ctx *ctx, vgb_index_view *view);
+int  vgb_index_upload_device(vgb_ctx *ctx, const vgb_index_view *device_view);   /* vgb_index_upload for records already in HBM */
+/* random upper-case ACGT contig text, twin of tools/synth.make_genome's base layer: base i of contig c =
+ * "ACGT"[(rnd64(seed, 1, c, i) >> 33) & 3] */
+int  vgb_synth_genome_device(vgb_ctx *ctx, uint8_t *device_out, const uint64_t *contig_starts, const uint64_t *contig_lens,
+                             uint32_t n_contigs, uint64_t seed);
 void *vgb_device_alloc(vgb_ctx *ctx, uint64_t bytes);
 void  vgb_device_free(vgb_ctx *ctx, void *p);
 int   vgb_memcpy_d2h(vgb_ctx *ctx, void *dst, const void *src_device, uint64_t bytes);

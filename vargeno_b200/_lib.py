@@ -48,7 +48,8 @@ SYMBOLS = ["vgb_abi_version", "vgb_ctx_create", "vgb_ctx_destroy", "vgb_last_err
            "vgb_site_count", "vgb_fetch_sites", "vgb_pinned_buffer", "vgb_submit_fastq", "vgb_submit_fastq_device", "vgb_sync",
            "vgb_reset_counts", "vgb_fetch_read_results", "vgb_lookup_kmers", "vgb_allreduce_pileup", "vgb_fetch_pileup",
            "vgb_call", "vgb_counter_device_ptr", "vgb_get_stats", "vgb_probe_bench", "vgb_random_sector_bench",
-           "vgb_synth_reads_device", "vgb_device_alloc", "vgb_device_free", "vgb_memcpy_d2h", "vgb_memcpy_h2d"]
+           "vgb_synth_reads_device", "vgb_device_alloc", "vgb_device_free", "vgb_memcpy_d2h", "vgb_memcpy_h2d",
+           "vgb_build_index_device", "vgb_free_index_device", "vgb_index_upload_device", "vgb_synth_genome_device"]
 
 _lib = None
 
@@ -90,6 +91,10 @@ def load():
         "vgb_device_free": (None, [vp, vp]),
         "vgb_memcpy_d2h": (i32, [vp, vp, vp, u64]),
         "vgb_memcpy_h2d": (i32, [vp, vp, vp, u64]),
+        "vgb_build_index_device": (i32, [vp, vp, u64, vp, vp, u32, vp, vp, vp, vp, u64, vp, u64, C.POINTER(IndexView)]),
+        "vgb_free_index_device": (None, [vp, C.POINTER(IndexView)]),
+        "vgb_index_upload_device": (i32, [vp, C.POINTER(IndexView)]),
+        "vgb_synth_genome_device": (i32, [vp, vp, vp, vp, u32, u64]),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)           # AttributeError if the library does not export what the header declares

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libvgb200.so")
 HOST_BIN = os.path.join(HERE, "vargeno-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU = ["vgb_api.cu", "vgb_index.cu", "vgb_fastq.cu", "vgb_geno.cu", "vgb_call.cu", "vgb_bench.cu"]
+CU = ["vgb_api.cu", "vgb_index.cu", "vgb_fastq.cu", "vgb_geno.cu", "vgb_call.cu", "vgb_bench.cu", "vgb_build.cu"]
 CPP = ["vgb_tables.cpp", "vgb_nccl.cpp"]
 HOST_CPP = ["host/vargeno_main.cpp", "host/geno_host.cpp"]
 HEADERS = ["vgb_common.cuh", "vgb_internal.h", "vgb_geno8.inl", os.path.join("..", "..", "include", "vgb200.h"), "host/geno_host.h"]

@@ -393,6 +393,42 @@ int vgb_synth_reads_device(vgb_ctx *c, const uint8_t *hap0, const uint8_t *hap1,
 	                   lowq_prob, lowq_chars, out, out_cap);
 }
 
+int vgb_build_index_device(vgb_ctx *c, const uint8_t *device_genome, uint64_t genome_len, const uint64_t *cstart, const uint64_t *clen,
+                           uint32_t n_contigs, const uint32_t *snp_pos0, const uint8_t *snp_code, const uint8_t *snp_rf, const uint8_t *snp_af,
+                           uint64_t n_snp_lines, const uint32_t *bf_pos0, uint64_t n_bf_lines, vgb_index_view *out)
+{
+	if (!c || !device_genome || !cstart || !clen || !out || n_contigs == 0) return VGB_E_ARG;
+	if (n_snp_lines && (!snp_pos0 || !snp_code || !snp_rf || !snp_af)) return VGB_E_ARG;
+	if (n_bf_lines && !bf_pos0) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return build_index_device(c, device_genome, genome_len, cstart, clen, n_contigs, snp_pos0, snp_code, snp_rf, snp_af, n_snp_lines,
+	                          bf_pos0, n_bf_lines, out);
+}
+
+void vgb_free_index_device(vgb_ctx *c, vgb_index_view *view)
+{
+	if (!c || !view) return;
+	cudaSetDevice(c->device);
+	free_index_device(view);
+}
+
+int vgb_index_upload_device(vgb_ctx *c, const vgb_index_view *device_view)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	c->upload_from_device = true;
+	const int rc = index_upload(c, device_view);
+	c->upload_from_device = false;
+	return rc;
+}
+
+int vgb_synth_genome_device(vgb_ctx *c, uint8_t *device_out, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs, uint64_t seed)
+{
+	if (!c || !device_out || !cstart || !clen) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return synth_genome(c, device_out, cstart, clen, n_contigs, seed);
+}
+
 void *vgb_device_alloc(vgb_ctx *c, uint64_t bytes)
 {
 	if (!c) return nullptr;

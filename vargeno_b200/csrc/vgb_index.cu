@@ -339,6 +339,13 @@ static const char *parse_err_text(uint32_t k)
 template <typename F>
 static int stream_records(vgb_ctx *c, const uint8_t *src, uint64_t n_rec, uint32_t rec_bytes, F launch)
 {
+	if (c->upload_from_device) {
+		// records already in HBM (vgb_build_index_device): convert in place, one launch, no staging
+		if (n_rec) { launch(const_cast<uint8_t *>(src), 0, n_rec); c->launches++; }
+		if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+			return set_err(c, VGB_E_CUDA, "index conversion kernel failed");
+		return VGB_OK;
+	}
 	const uint64_t piece_rec = (64ull << 20) / rec_bytes * 16;             // ~1 GiB pieces
 	uint8_t *h_pin[2] = { nullptr, nullptr }, *d_raw[2] = { nullptr, nullptr };
 	cudaEvent_t done[2];
@@ -395,7 +402,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	VGB_CUDA(c, cudaMemsetAsync(d_jg_lo, 0, ((1ull << 32) + 1) * 4, c->stream));
 	if ((rc = dev_alloc(c, &d_aux, v->n_ref_aux * AUX_COLS))) return rc;
 	VGB_CUDA(c, cudaMemsetAsync(d_jg, 0xFF, ((1ull << 32) + 1) * 4, c->stream));
-	if (v->n_ref_aux) VGB_CUDA(c, cudaMemcpyAsync(d_aux, v->ref_aux, v->n_ref_aux * AUX_COLS * 4, cudaMemcpyHostToDevice, c->stream));
+	if (v->n_ref_aux) VGB_CUDA(c, cudaMemcpyAsync(d_aux, v->ref_aux, v->n_ref_aux * AUX_COLS * 4, cudaMemcpyDefault, c->stream));
 	const uint32_t amb_lo = 0xFFFFFFFFu - (uint32_t)v->n_ref_aux;
 	rc = stream_records(c, v->ref_records, v->n_ref, 13, [&](uint8_t *d_raw, uint64_t first, uint64_t cnt) {
 		const uint64_t prev = first ? rd_kmer(v->ref_records + 13 * (first - 1)) : 0;
@@ -481,8 +488,8 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	uint32_t *d_rbf, *d_sbf;
 	if ((rc = dev_alloc(c, &d_rbf, rw * 2))) return rc;
 	if ((rc = dev_alloc(c, &d_sbf, sw * 2))) return rc;
-	if (rw) VGB_CUDA(c, cudaMemcpyAsync(d_rbf, v->ref_bf_words, rw * 8, cudaMemcpyHostToDevice, c->stream));
-	if (sw) VGB_CUDA(c, cudaMemcpyAsync(d_sbf, v->snp_bf_words, sw * 8, cudaMemcpyHostToDevice, c->stream));
+	if (rw) VGB_CUDA(c, cudaMemcpyAsync(d_rbf, v->ref_bf_words, rw * 8, cudaMemcpyDefault, c->stream));
+	if (sw) VGB_CUDA(c, cudaMemcpyAsync(d_sbf, v->snp_bf_words, sw * 8, cudaMemcpyDefault, c->stream));
 	ix.ref_bf = d_rbf; ix.ref_bf_bits = v->ref_bf_bits; ix.ref_bf_nw32 = rw * 2;
 	ix.snp_bf = d_sbf; ix.snp_bf_bits = v->snp_bf_bits; ix.snp_bf_nw32 = sw * 2;
 

@@ -54,6 +54,7 @@ struct vgb_ctx {
 	vgb_read_result *d_trace = nullptr;
 	uint64_t trace_cap = 0, trace_n = 0;
 	uint32_t sticky_format = 0;      // format error bits seen since the last reset
+	bool upload_from_device = false; // vgb_index_upload_device: the index view holds device pointers
 	void *d_spill = nullptr;         // per-warp overflow area for hit contexts
 	uint8_t *d_call_gt = nullptr;    // per-site output staging of vgb_call / vgb_fetch_pileup (allocated once, at first use)
 	double *d_call_conf = nullptr;
@@ -110,6 +111,12 @@ int random_sector_bench(vgb_ctx *c, uint64_t bytes, uint64_t n_loads, int repeat
 int synth_reads(vgb_ctx *c, const uint8_t *hap0, const uint8_t *hap1, uint64_t genome_len, const uint64_t *cstart,
                 const uint64_t *clen, uint32_t n_contigs, uint64_t n_reads, uint32_t read_len, uint64_t seed, uint64_t first_id,
                 uint32_t id_width, double sub_rate, double lowq_prob, uint32_t lowq_chars, char *out, uint64_t out_cap);
+// vgb_build.cu
+int build_index_device(vgb_ctx *c, const uint8_t *d_genome, uint64_t genome_len, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs,
+                       const uint32_t *snp_pos0, const uint8_t *snp_code, const uint8_t *snp_rf, const uint8_t *snp_af, uint64_t n_snp_lines,
+                       const uint32_t *bf_pos0, uint64_t n_bf_lines, vgb_index_view *out);
+void free_index_device(vgb_index_view *v);
+int synth_genome(vgb_ctx *c, uint8_t *d_out, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs, uint64_t seed);
 // vgb_nccl.cpp
 int nccl_unique_id(void *out128, std::string &err);
 int nccl_init(vgb_ctx *c);

@@ -225,6 +225,61 @@ class Genotyper:
                                                lowq_chars, C.c_void_p(out_d), out_cap))
 
 
+class DeviceIndex:
+    """Index records built in HBM by vgb_build_index_device (device pointers in the on-disk layouts)."""
+
+    def __init__(self, g: Genotyper, view: "_lib.IndexView", chr_names, chr_lens):
+        self.g, self.view, self.chr_names, self.chr_lens = g, view, list(chr_names), list(chr_lens)
+
+    def free(self):
+        if self.view is not None:
+            self.g.L.vgb_free_index_device(self.g.h, C.byref(self.view))
+            self.view = None
+
+    def to_host(self):
+        """Copy the records back: a tools.index_builder.Index, byte-identical to what `vargeno index` writes."""
+        from .tools import index_builder as ib
+        v, g = self.view, self.g
+        ref = g.d2h(v.ref_records, 13 * v.n_ref).view(ib.REF_REC) if v.n_ref else np.zeros(0, ib.REF_REC)
+        ref_aux = g.d2h(v.ref_aux, 40 * v.n_ref_aux).view("<u4").reshape(-1, 10) if v.n_ref_aux else np.zeros((0, 10), "<u4")
+        snp = g.d2h(v.snp_records, 16 * v.n_snp).view(ib.SNP_REC) if v.n_snp else np.zeros(0, ib.SNP_REC)
+        snp_aux = g.d2h(v.snp_aux, 78 * v.n_snp_aux).view(ib.SNP_AUX_REC) if v.n_snp_aux else np.zeros(0, ib.SNP_AUX_REC)
+        rbf = g.d2h(v.ref_bf_words, 8 * v.ref_bf_nwords).view("<u8")
+        sbf = g.d2h(v.snp_bf_words, 8 * v.snp_bf_nwords).view("<u8")
+        return ib.Index(ref, ref_aux, snp, snp_aux, v.ref_bf_bits, rbf, v.snp_bf_bits, sbf, self.chr_names, self.chr_lens)
+
+
+def build_index_device(g: Genotyper, genome_d: int, contig_names, contig_starts, contig_lens, snp_pos0, snp_ref_code, snp_alt_code,
+                       snp_ref_freq, snp_alt_freq, bf_pos0) -> DeviceIndex:
+    """vgb_build_index_device.  snp_*: the VCF lines that pass the dictionary-side filters (src/dictgen.c:599-748), file order,
+    positions 0-based in the concatenation; bf_pos0: the lines that pass the Bloom-filter-side filters (src/generate_bf.cc:224-241)."""
+    cs = np.ascontiguousarray(contig_starts, dtype="<u8")
+    cl = np.ascontiguousarray(contig_lens, dtype="<u8")
+    p0 = np.ascontiguousarray(snp_pos0, dtype="<u4")
+    code = np.ascontiguousarray((np.asarray(snp_ref_code, np.uint8) & 3) | (np.asarray(snp_alt_code, np.uint8) << 2), dtype="u1")
+    rf = np.ascontiguousarray(snp_ref_freq, dtype="u1")
+    af = np.ascontiguousarray(snp_alt_freq, dtype="u1")
+    bp = np.ascontiguousarray(bf_pos0, dtype="<u4")
+    view = _lib.IndexView()
+    g._ck(g.L.vgb_build_index_device(g.h, C.c_void_p(genome_d), int(cs[-1] + cl[-1]), _lib.ptr(cs), _lib.ptr(cl), cs.size, _lib.ptr(p0),
+                                     _lib.ptr(code), _lib.ptr(rf), _lib.ptr(af), p0.size, _lib.ptr(bp), bp.size, C.byref(view)))
+    return DeviceIndex(g, view, contig_names, [int(x) for x in cl])
+
+
+def upload_device_index(g: Genotyper, dix: DeviceIndex) -> None:
+    g._ck(g.L.vgb_index_upload_device(g.h, C.byref(dix.view)))
+    n = C.c_uint64()
+    g._ck(g.L.vgb_site_count(g.h, C.byref(n)))
+    g.n_sites = n.value
+    g.chr_names, g.chr_lens = list(dix.chr_names), list(dix.chr_lens)
+
+
+def synth_genome_device(g: Genotyper, out_d: int, contig_starts, contig_lens, seed: int) -> None:
+    cs = np.ascontiguousarray(contig_starts, dtype="<u8")
+    cl = np.ascontiguousarray(contig_lens, dtype="<u8")
+    g._ck(g.L.vgb_synth_genome_device(g.h, C.c_void_p(out_d), _lib.ptr(cs), _lib.ptr(cl), cs.size, seed))
+
+
 def gq(conf: float) -> int:
     """(int)(-1*10*log(conf)), src/qv.cc:1681 -- CPython's math.log is the C library's log."""
     return int(-10.0 * math.log(conf))

@@ -551,3 +551,38 @@ def build_index_from_arrays(names: Sequence[str], seqs: Sequence[np.ndarray], co
     ok &= np.asarray(ref_ascii) != np.asarray(alt_ascii)
     snp_bf = snp_bf_from_arrays(contig[ok], pos0[ok], pck)
     return Index(ref, ref_aux, snp, snp_aux, REF_BF_BITS, ref_bf, SNP_BF_BITS, snp_bf, list(names), [int(s.size) for s in seqs])
+
+
+def bf_line_positions(vcf_path: str, raw_names: Sequence[str], raw_seqs: Sequence[np.ndarray]):
+    """(contig index, 0-based position) of the VCF lines that reach the insert loop of constructBfFromVcf
+    (src/generate_bf.cc:203-246) apart from the N test of the preceding 32-mer, which the GPU builder does itself.
+    Same walk as build_snp_bf, including the stale-sequence behaviour for unknown contigs."""
+    out_c, out_p = [], []
+    pre, ci, seq = "XO", -1, np.zeros(0, np.uint8)
+    with open(vcf_path, "rb") as f:
+        for line in f.read().split(b"\n"):
+            if not line or line[:1] == b"#":
+                continue
+            col = line.split(b"\t")
+            chrom = col[0].decode("latin-1")
+            if chrom[:1] != "c":
+                chrom = "chr" + chrom
+            pos = int(re.match(rb"\s*[+-]?\d+", col[1]).group(0)) - 1
+            r, a = col[3], col[4]
+            if len(r) > 1 or len(a) > 1:
+                continue
+            if chrom != pre:
+                for k, (nm, s) in enumerate(zip(raw_names, raw_seqs)):
+                    if nm == chrom:
+                        seq, ci = s, k
+                        break
+                pre = chrom
+            if pos < 32 or pos + 32 > seq.size:
+                continue
+            if r[0] != seq[pos] or r == a or a in (b"N", b"n"):
+                continue
+            if _CODE[a[0]] == 7:
+                raise ValueError("ALT base %r makes the reference abort in shift_kmer (src/util.c:122)" % a)
+            out_c.append(ci)
+            out_p.append(pos)
+    return np.array(out_c, np.int64), np.array(out_p, np.int64)
