@@ -182,6 +182,8 @@ void *vgb_device_alloc(vgb_ctx *ctx, uint64_t bytes);
 void  vgb_device_free(vgb_ctx *ctx, void *p);
 int   vgb_memcpy_d2h(vgb_ctx *ctx, void *dst, const void *src_device, uint64_t bytes);
 int   vgb_memcpy_h2d(vgb_ctx *ctx, void *dst_device, const void *src, uint64_t bytes);
+int   vgb_memcpy_d2d(vgb_ctx *ctx, void *dst_device, const void *src_device, uint64_t bytes);
+int   vgb_memset_device(vgb_ctx *ctx, void *dst_device, int value, uint64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,31 @@ def test_device_resident_upload_equals_host_upload(cache):
         assert np.array_equal(want_sites[k], got_sites[k]), k
 
 
+def test_device_workload_matches_numpy_builder():
+    """tools/device_workloads.build (genome layout, SNP filters and index all via the GPU) gives the index the numpy builder
+    -- itself pinned to the reference -- gives for the same genome and SNP list."""
+    from vargeno_b200.geno import Genotyper
+    from vargeno_b200.tools import device_workloads as dw
+    from vargeno_b200.tools import synth, workloads
+    contigs = [("chr1", 300000), ("chr2", 180000), ("chrM", 16571)]
+    with Genotyper(device=0) as g:
+        wl = dw.build(g, contigs, 3000, seed=5, name="t", keep_host=True)
+        assert g.n_sites > 2000
+    g0 = synth.make_genome(contigs, seed=5)
+    cat = g0.concat().copy()
+    dw.apply_layout_host(cat, dw.repeat_ops(cat.size, 5, 0.02), dw.n_blocks(wl.starts, wl.lens, 0.05))
+    assert np.array_equal(cat, wl.host_genome)
+    seqs = [cat[s:s + l] for s, l in zip(wl.starts, wl.lens)]
+    snps = synth.make_snps(synth.Genome(wl.names, seqs), 3000, seed=5)
+    f1, f2 = workloads.caf_pair(snps)
+    want = ib.build_index_from_arrays(wl.names, seqs, snps.contig, snps.pos0, snps.ref, snps.alt, f1, f2)
+    got = wl.host_index
+    assert want.ref_aux.shape[0] > 0, "repeat families should create aux rows"
+    for f in ("ref", "ref_aux", "snp", "snp_aux", "snp_bf"):
+        assert np.array_equal(getattr(want, f), getattr(got, f)), f
+    assert np.array_equal(np.flatnonzero(want.ref_bf), np.flatnonzero(got.ref_bf[:want.ref_bf.size]))
+
+
 def test_device_genome_generator_matches_numpy():
     from vargeno_b200 import geno
     from vargeno_b200.geno import Genotyper

@@ -454,6 +454,22 @@ int vgb_memcpy_d2h(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
 	return VGB_OK;
 }
 
+int vgb_memcpy_d2d(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+	return VGB_OK;
+}
+
+int vgb_memset_device(vgb_ctx *c, void *dst, int value, uint64_t bytes)
+{
+	if (!c) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaMemset(dst, value, bytes));
+	return VGB_OK;
+}
+
 int vgb_memcpy_h2d(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
 {
 	if (!c) return VGB_E_ARG;
