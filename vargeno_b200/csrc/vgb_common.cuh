@@ -48,7 +48,9 @@ struct DevIndex {
 	const RefEntry *ref_by_lo;  // {HI32(kmer), posx}, bucket order unspecified
 	const uint32_t *ref_jg_lo;  // 2^32 entries: END of the bucket of LO32 == l (start = end of bucket l-1, 0 for l == 0)
 	const SnpEntry *snp;        uint64_t n_snp;
-	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678)
+	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678): the HI24 block the strided scan needs
+	const uint32_t *snp_jg30;   // 2^30 + 1 entries, same idea on the top 30 bits: exact queries land in a block of ~0-2 entries
+	                            // (a GRCh38-sized SNP dictionary has ~23 entries per HI24 block = 4-5 dependent sectors per query)
 	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
 	const uint32_t *ref_bf;     uint64_t ref_bf_bits; uint64_t ref_bf_nw32;
 	const uint32_t *snp_bf;     uint64_t snp_bf_bits; uint64_t snp_bf_nw32;
@@ -159,10 +161,17 @@ __device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_
 	}
 	return -1;
 }
+// block of the top 30 bits: only for exact membership (entry rank inside the HI24 block is not needed there)
+__device__ __forceinline__ void snp_block30(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
+{
+	const uint64_t h = kmer >> 34;
+	lo = __ldg(ix.snp_jg30 + h);
+	hi = __ldg(ix.snp_jg30 + h + 1);
+}
 __device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
 {
 	uint32_t lo, hi;
-	snp_block(ix, kmer, lo, hi);
+	snp_block30(ix, kmer, lo, hi);
 	if (lo >= hi) return -1;
 	return snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, lo, hi, out);
 }

@@ -206,14 +206,16 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			// ---- level 1: everything that depends only on the k-mer is put in flight together ----
 			const bool mine = run && ol < K;
 			uint32_t rlo = 0, rhi = 0, slo = 0, shi = 0, bfr_w = 0, bfs_w = 0, bs = 0, be = 0;
+			uint32_t f_lo = 0, f_hi = 0;                       // SNP block of the top 30 bits: exact membership only
 			uint64_t bfr_bit = 0, bfs_bit = 0;
 			const bool gates = mine && lowq;
 			if (mine) {
 				ref_block(ix, kmer, rlo, rhi);
-				snp_block(ix, kmer, slo, shi);
+				snp_block30(ix, kmer, f_lo, f_hi);
 				atomicAdd(&os->st[S_EXACT], 2u);
 			}
 			if (gates) {
+				snp_block(ix, kmer, slo, shi);                 // HI24 block: the strided scan walks it by rank (F13)
 				bfr_bit = hash32((uint32_t)kmer);
 				if (ix.ref_bf_bits <= 0xFFFFFFFFull) bfr_bit %= ix.ref_bf_bits;
 				bfs_bit = hash40(kmer & 0xFFFFFFFFFFull) % ix.snp_bf_bits;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				uint32_t posx = 0;
 				SnpEntry e;
 				if (rlo < rhi && ref_find_in_block(ix, (uint32_t)kmer, rlo, rhi, posx) >= 0) exact_ref_events8(ix, os, kmer, posx, 32u * ol, ol, rs);
-				if (slo < shi && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, slo, shi, e) >= 0) exact_snp_events8(ix, os, kmer, e, 32u * ol, ol, rs);
+				if (f_lo < f_hi && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, f_lo, f_hi, e) >= 0) exact_snp_events8(ix, os, kmer, e, 32u * ol, ol, rs);
 			}
 			const bool rb = gates && ((bfr_w >> (bfr_bit & 31)) & 1u);
 			const bool sb = gates && ((bfs_w >> (bfs_bit & 31)) & 1u);

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_max_u32(const uint32_t *a, uint64_t n, 
 
 // raw: 16-byte records (aligned)
 __global__ void __launch_bounds__(256) k_parse_snp(const uint4 *raw, uint64_t first, uint64_t count, uint64_t prev_kmer,
-                                                    SnpEntry *out, uint32_t *jg, uint32_t n_aux, uint32_t *last_writer,
+                                                    SnpEntry *out, uint32_t *jg, uint32_t *jg30, uint32_t n_aux, uint32_t *last_writer,
                                                     uint64_t pile_len, ParseOut *po)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(256) k_parse_snp(const uint4 *raw, uint64_t fi
 	out[g] = e;
 	const uint32_t hi = (uint32_t)(kmer >> 40);
 	if (g == 0 || (uint32_t)(pk >> 40) != hi) jg[hi] = (uint32_t)g;
+	if (g == 0 || (pk >> 34) != (kmer >> 34)) jg30[kmer >> 34] = (uint32_t)g;
 	// static pileup writer (src/qv.cc:637-659): unambiguous, reference base in ACGT; file order, last wins
 	if ((info & 4) == 0 && pos != POS_AMBIGUOUS && flag == 0) {
 		const uint64_t sp = (uint64_t)pos + ipos;
@@ -425,9 +426,11 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	// ---- SNP dictionary + static pileup ----
 	// SNP k-mer starts are reference k-mer starts, so sites lie below max_pos + 32 (src/qv.cc:596-603)
 	const uint64_t pile_len = (((uint64_t)po.max_pos + 32 + 1) + 63) / 64 * 64;
-	SnpEntry *d_snp; uint32_t *d_sjg, *d_sap, *d_lw; uint8_t *d_sai;
+	SnpEntry *d_snp; uint32_t *d_sjg, *d_sjg30, *d_sap, *d_lw; uint8_t *d_sai;
 	if ((rc = dev_alloc(c, &d_snp, v->n_snp))) return rc;
 	if ((rc = dev_alloc(c, &d_sjg, (1ull << 24) + 1))) return rc;
+	if ((rc = dev_alloc(c, &d_sjg30, (1ull << 30) + 1))) return rc;
+	VGB_CUDA(c, cudaMemsetAsync(d_sjg30, 0xFF, ((1ull << 30) + 1) * 4, c->stream));
 	if ((rc = dev_alloc(c, &d_sap, v->n_snp_aux * AUX_COLS))) return rc;
 	if ((rc = dev_alloc(c, &d_sai, v->n_snp_aux * AUX_COLS))) return rc;
 	if ((rc = dev_alloc(c, &d_lw, pile_len, false))) return rc;
@@ -437,7 +440,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	rc = stream_records(c, v->snp_records, v->n_snp, 16, [&](uint8_t *d_raw, uint64_t first, uint64_t cnt) {
 		const uint64_t prev = first ? rd_kmer(v->snp_records + 16 * (first - 1)) : 0;
 		k_parse_snp<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint4 *>(d_raw), first, cnt, prev, d_snp, d_sjg,
-		                                                                  (uint32_t)v->n_snp_aux, d_lw, pile_len, d_po);
+		                                                                  d_sjg30, (uint32_t)v->n_snp_aux, d_lw, pile_len, d_po);
 	});
 	if (rc) return rc;
 	if (v->n_snp_aux) {
@@ -447,6 +450,8 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 		if (rc) return rc;
 	}
 	if ((rc = fill_jumpgate(c, d_sjg, 24, (uint32_t)v->n_snp, d_tmp))) return rc;
+	if ((rc = fill_jumpgate(c, d_sjg30, 30, (uint32_t)v->n_snp, d_tmp))) return rc;
+	ix.snp_jg30 = d_sjg30;
 	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "SNP dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	ix.snp = d_snp; ix.n_snp = v->n_snp; ix.snp_jg = d_sjg; ix.snp_aux_pos = d_sap; ix.snp_aux_info = d_sai; ix.n_snp_aux = (uint32_t)v->n_snp_aux;
