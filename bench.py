@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 REC_ID_WIDTH = 9
+S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS = 0.005, 0.25, 4
 
 
 def rec_bytes(read_len):
@@ -112,7 +113,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from vargeno_b200.geno import Genotyper
-    from vargeno_b200.tools import workloads
+    from vargeno_b200.tools import device_workloads as dw
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -124,8 +125,7 @@ def run_ours(args):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     K, W, B = args.steps, args.warmup, args.batch_reads
     t_setup = time.time()
-    wl = workloads.make_s1(scale=args.scale)
-    L = wl.read_len
+    L = 150
     batch_bytes = B * rec_bytes(L)
     nb = K + W
 
@@ -135,21 +135,17 @@ def run_ours(args):
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
     g = Genotyper(device=local, max_chunk_bytes=batch_bytes + 4096, world_size=world, rank=rank, nccl_unique_id=uid)
-    g.upload_index(wl.index)
+    # S1 index: genome text, SNP list, reference-format index records and the GPU re-layout, all produced through the device
+    # (vgb_build_index_device is byte-identical to `vargeno index`: tests/test_gpu_index_build.py); replicated on every rank
+    want_cpu = rank == 0 and world == 1 and not args.skip_cpu
+    wl = dw.build_s1(g, scale=args.scale, keep_host=want_cpu)
     if world > 1:
         g.allreduce()                       # NCCL connection set-up happens on the first collective: keep it out of the timed legs
 
     # synthetic reads, generated on the device (byte-identical twin of tools/synth.simulate_reads)
-    h0 = g.dalloc(wl.haps[0].size)
-    h1 = g.dalloc(wl.haps[1].size)
-    g.h2d(h0, wl.haps[0])
-    g.h2d(h1, wl.haps[1])
     d_reads = g.dalloc(nb * batch_bytes)
     first = rank * nb * B
-    g.synth_reads_device(h0, h1, wl.haps[0].size, wl.genome.starts, wl.genome.lengths, nb * B, L, wl.seed + 1000, first,
-                         REC_ID_WIDTH, wl.sub_rate, wl.lowq_prob, wl.lowq_chars, d_reads, nb * batch_bytes)
-    g.dfree(h0)
-    g.dfree(h1)
+    dw.synth_batch(g, wl, d_reads, nb * B, first, S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS, REC_ID_WIDTH)
     # host copy in pinned memory for the end-to-end leg
     pinned = torch.empty(nb * batch_bytes, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
@@ -237,7 +233,7 @@ def run_ours(args):
                 rs = None
         cpu = None
         if world == 1 and not args.skip_cpu:
-            cpu = cpu_port_baseline(wl, host[:min(B, args.cpu_sample) * rec_bytes(L)])
+            cpu = cpu_port_baseline(wl.host_index, host[:min(B, args.cpu_sample) * rec_bytes(L)])
         out = {
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -246,7 +242,8 @@ def run_ours(args):
                        "reads_per_step_per_gpu": B, "read_len": L, "fastq_bytes_per_step_per_gpu": batch_bytes,
                        "index": "replicated per GPU", "reads": "sharded across GPUs",
                        "l2": "every step streams a distinct batch larger than L2 (no flush needed)",
-                       "ref_kmers": int(wl.index.ref.size), "snp_kmers": int(wl.index.snp.size), "snp_sites": int(n_sites)},
+                       "ref_kmers": wl.index_counts["ref_kmers"], "snp_kmers": wl.index_counts["snp_kmers"], "snp_sites": int(n_sites),
+                       "index_built_by": "vgb_build_index_device (byte-identical to `vargeno index`)"},
             "kmer_lookups_per_s": d_lookups * world / dt if world == 1 else None,
             "lookups_per_read": d_lookups / max(1, st1["reads"] - st0["reads"]),
             "placed_fraction": (st1["placed"] - st0["placed"]) / max(1, st1["reads"] - st0["reads"]),
@@ -272,10 +269,10 @@ def run_ours(args):
     return out
 
 
-def cpu_port_baseline(wl, text):
+def cpu_port_baseline(index, text):
     """Bounded single-thread run of the CPU oracle (kind "port") over a prefix of the same reads."""
     from oracle import oracle as orc
-    o = orc.Oracle(wl.index)
+    o = orc.Oracle(index)
     t0 = time.perf_counter()
     o.process_fastq(np.ascontiguousarray(text), want_results=False)
     dt = time.perf_counter() - t0
@@ -301,8 +298,7 @@ def run_reference(args):
     from vargeno_b200.tools import synth, workloads
 
     K, W = args.steps, args.warmup
-    wl = workloads.make_s1(scale=args.scale)
-    L = wl.read_len
+    L = 150
     Bp = args.ref_batch_reads
     try:
         avail_gb = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) / 1e6
@@ -314,30 +310,33 @@ def run_reference(args):
         nproc = args.ref_procs
     nb = K + W
 
-    # reads: distinct per process and step
+    # index + reads (distinct per process and step).  With a GPU on the box they come from the device-side builder (seconds,
+    # byte-identical index); without one, from the numpy tooling.  Neither is part of what is timed.
     total = nproc * nb * Bp
-    text = None
+    index, text, name = None, None, None
     try:
         import torch
         if torch.cuda.is_available():
             from vargeno_b200.geno import Genotyper
+            from vargeno_b200.tools import device_workloads as dw
             with Genotyper(device=0) as g:
-                h0, h1, out = g.dalloc(wl.haps[0].size), g.dalloc(wl.haps[1].size), g.dalloc(total * rec_bytes(L))
-                g.h2d(h0, wl.haps[0])
-                g.h2d(h1, wl.haps[1])
-                g.synth_reads_device(h0, h1, wl.haps[0].size, wl.genome.starts, wl.genome.lengths, total, L, wl.seed + 1000, 0,
-                                     REC_ID_WIDTH, wl.sub_rate, wl.lowq_prob, wl.lowq_chars, out, total * rec_bytes(L))
+                dwl = dw.build_s1(g, scale=args.scale, keep_host=True)
+                out = g.dalloc(total * rec_bytes(L))
+                dw.synth_batch(g, dwl, out, total, 0, S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS, REC_ID_WIDTH)
                 text = g.d2h(out, total * rec_bytes(L))
+                index, name = dwl.host_index, dwl.name
     except Exception:
-        text = None
+        index, text = None, None
     if text is None:
-        text = synth.simulate_reads(wl.genome, wl.haps, total, L, seed=wl.seed + 1000, sub_rate=wl.sub_rate, lowq_prob=wl.lowq_prob,
-                                    lowq_chars=wl.lowq_chars, id_width=REC_ID_WIDTH)
+        wl = workloads.make_s1(scale=args.scale)
+        index, name = wl.index, wl.name
+        text = synth.simulate_reads(wl.genome, wl.haps, total, L, seed=wl.seed + 1000, sub_rate=S1_SUB_RATE, lowq_prob=S1_LOWQ_PROB,
+                                    lowq_chars=S1_LOWQ_CHARS, id_width=REC_ID_WIDTH)
     bb = Bp * rec_bytes(L)
 
     if not use_ref:
         # the oracle port, one thread (the compiled reference is absent or would not fit in RAM)
-        o = orc.Oracle(wl.index)
+        o = orc.Oracle(index)
         times = []
         for s in range(nb):
             t0 = time.perf_counter()
@@ -349,9 +348,9 @@ def run_reference(args):
     else:
         d = tempfile.mkdtemp(prefix="vg_refarm_")
         prefix = os.path.join(d, "s1")
-        ib.write_index(wl.index, prefix)
-        vcf = os.path.join(d, "snp.vcf")
-        synth.write_vcf(wl.genome, wl.snps, vcf)
+        ib.write_index(index, prefix)
+        vcf = os.path.join(d, "snp.vcf")            # only opened after the read loop (src/qv.cc:1628), which this arm never reaches
+        open(vcf, "w").write("##fileformat=VCFv4.0\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
         procs, fifos, fds = [], [], []
         for p in range(nproc):
             ff = os.path.join(d, "reads%d.fq" % p)
@@ -400,7 +399,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
            "data": "synthetic",
-           "config": {"workload": wl.name + ", 1M-SNP list, 150bp reads @0.5% subst, lowq 0.25 on first 4 quality chars",
+           "config": {"workload": name + ", 1M-SNP list, 150bp reads @0.5% subst, lowq 0.25 on first 4 quality chars",
                       "reads_per_step": Bp * cores, "read_len": L},
            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

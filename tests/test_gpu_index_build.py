@@ -103,6 +103,23 @@ def test_device_workload_matches_numpy_builder():
     assert np.array_equal(np.flatnonzero(want.ref_bf), np.flatnonzero(got.ref_bf[:want.ref_bf.size]))
 
 
+def test_device_s1_equals_numpy_s1():
+    """bench.py builds S1 through the device; it must be the S1 of tools/workloads.make_s1 (genome, haplotypes, index)."""
+    from vargeno_b200.geno import Genotyper
+    from vargeno_b200.tools import device_workloads as dw
+    from vargeno_b200.tools import workloads
+    want = workloads.make_s1(scale=0.004)
+    with Genotyper(device=0) as g:
+        wl = dw.build_s1(g, scale=0.004, keep_host=True)
+        h0 = g.d2h(wl.hap0_d, wl.genome_len)
+        h1 = g.d2h(wl.hap1_d, wl.genome_len)
+    assert np.array_equal(wl.host_genome, want.genome.concat())
+    assert np.array_equal(h0, want.haps[0]) and np.array_equal(h1, want.haps[1])
+    for f in ("ref", "ref_aux", "snp", "snp_aux", "snp_bf"):
+        assert np.array_equal(getattr(want.index, f), getattr(wl.host_index, f)), f
+    assert np.array_equal(np.flatnonzero(want.index.ref_bf), np.flatnonzero(wl.host_index.ref_bf))
+
+
 def test_device_genome_generator_matches_numpy():
     from vargeno_b200 import geno
     from vargeno_b200.geno import Genotyper

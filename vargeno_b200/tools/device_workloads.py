@@ -97,7 +97,9 @@ def _dict_side_ok(cat: np.ndarray, g: np.ndarray, chunk: int = 1 << 20) -> np.nd
 
 
 def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, seed: int, name: str, n_frac: float = 0.05,
-          repeat_frac: float = 0.02, read_len: int = 150, keep_host: bool = False, verbose: bool = False) -> DeviceWorkload:
+          repeat_frac: float = 0.02, read_len: int = 150, keep_host: bool = False, verbose: bool = False,
+          blocks: Optional[List[Tuple[int, int]]] = None) -> DeviceWorkload:
+    """blocks: explicit (global start, length) N runs instead of the n_frac layout."""
     t = {}
     t0 = time.time()
     names = [n for n, _ in contigs]
@@ -109,7 +111,8 @@ def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, 
     ops = repeat_ops(total, seed, repeat_frac)
     for src, dst, ln in ops:
         g._ck(g.L.vgb_memcpy_d2d(g.h, gd + dst, gd + src, ln))
-    blocks = n_blocks(starts, lens, n_frac)
+    if blocks is None:
+        blocks = n_blocks(starts, lens, n_frac)
     for s, l in blocks:
         g._ck(g.L.vgb_memset_device(g.h, gd + s, ord("N"), l))
     t["genome_s"] = time.time() - t0
@@ -144,6 +147,16 @@ def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, 
         print("device workload %s: %s %s" % (name, counts, {k: round(v, 2) for k, v in t.items()}), flush=True)
     return DeviceWorkload(name, names, starts, lens, total, h0d, h1d, read_len, seed, int(dict_ok.sum()), counts, t,
                           cat if keep_host else None, host_index)
+
+
+def build_s1(g: "geno.Genotyper", scale: float = 1.0, seed: int = 7, keep_host: bool = False, verbose: bool = False) -> DeviceWorkload:
+    """The S1 workload of tools/workloads.make_s1 (same genome, same SNP list, same index, byte for byte), built through the
+    GPU in a few seconds instead of ~50 s of numpy."""
+    L = int(50_800_000 * scale)
+    n_snps = int(1_000_000 * scale)
+    blocks = [(0, int(L * 0.19)), (int(L * 0.45), int(L * 0.02)), (int(L * 0.93), int(L * 0.006))]
+    return build(g, [("chr22", L)], n_snps, seed, "S1 chr22-shaped x%g" % scale, repeat_frac=0.0, keep_host=keep_host, verbose=verbose,
+                 blocks=blocks)
 
 
 def synth_batch(g: "geno.Genotyper", wl: DeviceWorkload, out_d: int, n_reads: int, first_id: int, sub_rate: float, lowq_prob: float,
