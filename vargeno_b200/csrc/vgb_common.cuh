@@ -51,6 +51,10 @@ struct DevIndex {
 	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678): the HI24 block the strided scan needs
 	const uint32_t *snp_jg30;   // 2^30 + 1 entries, same idea on the top 30 bits: exact queries land in a block of ~0-2 entries
 	                            // (a GRCh38-sized SNP dictionary has ~23 entries per HI24 block = 4-5 dependent sectors per query)
+	// residue-major copy of the LO40 column for the strided scan (F13): step t of a scan that starts at rank lo examines rank
+	// lo + 11 t, i.e. one residue class mod 11 at consecutive quotients -- stored contiguously here, so the ~23 steps of a
+	// GRCh38-sized block touch ~6 sectors instead of 23:  snp_scan[(r % 11) * snp_scan_stride + r / 11] = LO40(entry r)
+	const uint64_t *snp_scan;   uint64_t snp_scan_stride;
 	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
 	const uint32_t *ref_bf;     uint64_t ref_bf_bits; uint64_t ref_bf_nw32;
 	const uint32_t *snp_bf;     uint64_t snp_bf_bits; uint64_t snp_bf_nw32;
@@ -160,6 +164,11 @@ __device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_
 		if ((key & M40) == key_lo40) { out.key = key; out.pos = e.z; out.extra = e.w; return (int64_t)i; }
 	}
 	return -1;
+}
+// LO40 of SNP entry (lo + 11 s): what step s of the reference's strided scan over the block starting at rank lo examines
+__device__ __forceinline__ uint64_t snp_scan_lo40(const DevIndex &ix, uint32_t lo, uint32_t s)
+{
+	return __ldg(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
 }
 // block of the top 30 bits: only for exact membership (entry rank inside the HI24 block is not needed there)
 __device__ __forceinline__ void snp_block30(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)

@@ -270,6 +270,12 @@ __global__ void __launch_bounds__(256) k_parse_snp(const uint4 *raw, uint64_t fi
 	if (err) { atomicAdd(&po->errors, 1ull); atomicCAS(&po->first_error_kind, 0u, err); }
 }
 
+__global__ void __launch_bounds__(256) k_snp_scan_layout(const SnpEntry *snp, uint64_t n, uint64_t stride, uint64_t *scan)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n) scan[(r % SNP_STRIDE) * stride + r / SNP_STRIDE] = snp[r].key & 0xFFFFFFFFFFull;
+}
+
 __global__ void __launch_bounds__(256) k_snp_aux(const uint8_t *raw78, uint64_t n, uint32_t *pos_out, uint8_t *info_out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, col)
@@ -452,6 +458,16 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	if ((rc = fill_jumpgate(c, d_sjg, 24, (uint32_t)v->n_snp, d_tmp))) return rc;
 	if ((rc = fill_jumpgate(c, d_sjg30, 30, (uint32_t)v->n_snp, d_tmp))) return rc;
 	ix.snp_jg30 = d_sjg30;
+	{
+		// residue-major LO40 column for the strided scan
+		const uint64_t stride = (v->n_snp + SNP_STRIDE - 1) / SNP_STRIDE + 1;
+		uint64_t *d_scan;
+		if ((rc = dev_alloc(c, &d_scan, stride * SNP_STRIDE))) return rc;
+		VGB_CUDA(c, cudaMemsetAsync(d_scan, 0, stride * SNP_STRIDE * 8, c->stream));
+		if (v->n_snp) k_snp_scan_layout<<<(unsigned)((v->n_snp + 255) / 256), 256, 0, c->stream>>>(d_snp, v->n_snp, stride, d_scan);
+		c->launches++;
+		ix.snp_scan = d_scan; ix.snp_scan_stride = stride;
+	}
 	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "SNP dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	ix.snp = d_snp; ix.n_snp = v->n_snp; ix.snp_jg = d_sjg; ix.snp_aux_pos = d_sap; ix.snp_aux_info = d_sai; ix.n_snp_aux = (uint32_t)v->n_snp_aux;
