@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvgb200.so")
+# VGB200_LIB: A/B measurements of two builds of the same library (tools/perf_sweep.py); never a different implementation
+LIB_PATH = os.environ.get("VGB200_LIB") or os.path.join(HERE, "libvgb200.so")
 
 VGB_OK, VGB_E_ARG, VGB_E_CUDA, VGB_E_FORMAT, VGB_E_INDEX, VGB_E_NCCL, VGB_E_OVERFLOW = 0, -1, -2, -3, -4, -5, -6
 VGB_CFG_TRACE = 1

@@ -49,7 +49,6 @@ struct GenoArgs {
 	Event *spill;                 // [grid warps][EV_CAP - EV_SMEM]
 	const uint32_t *list;         // warp kernel: nullptr = every read of the chunk, else the deferred reads (count in meta[6])
 	uint32_t *defer;              // 8-lane kernel: where deferred read indices go
-	uint32_t debug_stage;         // VGB_DEBUG_STAGE: stop the 8-lane kernel after a phase (bring-up aid), 0 = run everything
 };
 
 struct LaneStats {
@@ -182,7 +181,9 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 		if (r0 >= n_reads) break;
 		const uint32_t r1 = min(r0 + READ_BATCH, n_reads);
 		for (uint32_t ri = r0; ri < r1; ri++) {
-			const uint32_t r = a.list ? __ldg(a.list + ri) : ri;
+			// list entries: bit 31 = the 8-lane kernel already ran (and accounted for) the forward pass, start at the retry
+			const uint32_t rr = a.list ? __ldg(a.list + ri) : ri;
+			const uint32_t r = rr & 0x7FFFFFFFu;
 			// ---- record framing: lines 4r .. 4r+3 (src/qv.cc:760-779) ----
 			uint32_t lsv = lane < 5 ? __ldg(a.line_start + 4ull * r + lane) : 0;
 			const uint32_t id_s = __shfl_sync(0xffffffffu, lsv, 0);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 
 			bool process = false, has_best = false, ambiguous = false;
 			uint32_t target = 0, best_freq = 0, E = 0;
-			uint32_t pass = 0;
+			uint32_t pass = a.list ? rr >> 31 : 0u;
 			for (;; pass++) {
 				if (pass == 1) {                                   // src/qv.cc:787-806: reverse complement of the first 32K bases
 					const uint64_t o = __shfl_sync(0xffffffffu, kmer_fwd, (K - 1 - lane) & 31);
@@ -490,31 +491,34 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 #include "vgb_geno8.inl"
 
 typedef void (*geno_kernel_t)(const GenoArgs);
-static geno_kernel_t g_warp_kernel = nullptr, g_oct_kernel = nullptr;
-static uint32_t g_oct_grid = 0, g_debug_stage = 0;
+static geno_kernel_t g_warp_kernel = nullptr, g_oct_kernel = nullptr, g_oct_kernel_trace = nullptr;
+static size_t oct_smem_bytes() { return sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t) + sizeof(Pend) * GW * PEND_CAP; }
+static uint32_t g_oct_grid = 0;
 
 int geno_prepare(vgb_ctx *c)
 {
 	// VGB_GENO_KERNEL=warp: one warp per read for everything (the first version, kept as the path for deferred reads)
 	// VGB_GENO_MINB / VGB_GENO8_MINB: register budget variants (CTAs per SM the compiler must make room for)
-	int minb = 4, minb8 = 6;     // measured on B200 (profiles/r01_summary.md): 40 registers / 48 warps per SM is the sweet spot (8 CTAs/SM spills too much)
+	int minb = 4, minb8 = 4;     // measured on B200 (profiles/r01_summary.md): 62 registers, no spills, 32 warps per SM beats 40 registers / 48 warps
 	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
 	if (const char *e = getenv("VGB_GENO8_MINB")) minb8 = atoi(e);
 	const char *kk = getenv("VGB_GENO_KERNEL");
 	const bool warp_only = kk && !strcmp(kk, "warp");
-	if (const char *e = getenv("VGB_DEBUG_STAGE")) g_debug_stage = (uint32_t)atoi(e);
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
-	geno_kernel_t k8 = minb8 >= 8 ? k_geno8<8> : (minb8 >= 6 ? k_geno8<6> : (minb8 == 5 ? k_geno8<5> : (minb8 == 3 ? k_geno8<3> : k_geno8<4>)));
+	geno_kernel_t k8 = minb8 >= 8 ? k_geno8<8, false> : (minb8 >= 6 ? k_geno8<6, false> : (minb8 == 5 ? k_geno8<5, false> : (minb8 == 3 ? k_geno8<3, false> : k_geno8<4, false>)));
+	geno_kernel_t k8t = minb8 >= 8 ? k_geno8<8, true> : (minb8 >= 6 ? k_geno8<6, true> : (minb8 == 5 ? k_geno8<5, true> : (minb8 == 3 ? k_geno8<3, true> : k_geno8<4, true>)));
 	g_warp_kernel = k;
 	g_oct_kernel = warp_only ? nullptr : k8;
+	g_oct_kernel_trace = warp_only ? nullptr : k8t;
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
 	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
-	const size_t smem8 = sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t);   // hit contexts + one row of counters per warp
+	const size_t smem8 = oct_smem_bytes();   // hit contexts + one row of counters per warp + the warp's parked reads
 	VGB_CUDA(c, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+	VGB_CUDA(c, cudaFuncSetAttribute(k8t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k8, GW * 32, smem8));
 	if (occ < 1) occ = 1;
 	g_oct_grid = (uint32_t)(c->sm_count * occ);
@@ -540,10 +544,10 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.spill = (Event *)c->d_spill;
 	a.list = nullptr;
 	a.defer = ck.d_defer;
-	a.debug_stage = g_debug_stage;
 	if (g_oct_kernel) {
 		// main kernel: 8 lanes per read; then the reads it deferred (long reads, context overflow) one warp per read
-		g_oct_kernel<<<g_oct_grid, GW * 32, sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t), c->stream>>>(a);
+		// per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernel carries none of it
+		(a.trace ? g_oct_kernel_trace : g_oct_kernel)<<<g_oct_grid, GW * 32, oct_smem_bytes(), c->stream>>>(a);
 		a.list = ck.d_defer;
 		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches += 2;
