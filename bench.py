@@ -150,6 +150,9 @@ def run_ours(args):
     pinned = torch.empty(nb * batch_bytes, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
     host[:] = g.d2h(d_reads, nb * batch_bytes)
+    # pinned destination of the job's result (GT + confidence per SNP site), allocated once like a real caller would
+    out_gt = torch.empty(g.n_sites, dtype=torch.uint8, pin_memory=True).numpy()
+    out_conf = torch.empty(g.n_sites, dtype=torch.float64, pin_memory=True).numpy()
     setup_s = time.time() - t_setup
 
     def barrier():
@@ -201,6 +204,8 @@ def run_ours(args):
     g.reset()
     for i in range(W):
         g.submit_chunk(host[i * batch_bytes:(i + 1) * batch_bytes], first + i * B)
+    g.sync()
+    g.call(out=(out_gt, out_conf))          # warm-up of the result path too (its device staging is allocated at first use)
     barrier()
     t0 = time.perf_counter()
     for i in range(W, nb):
@@ -210,7 +215,7 @@ def run_ours(args):
     if world > 1:
         g.allreduce()
     t_reduce = time.perf_counter() - t0 - t_reads
-    gt, conf = g.call()                     # device -> host read of the job's result (GT + confidence per SNP site)
+    gt, conf = g.call(out=(out_gt, out_conf))   # device -> host read of the job's result (GT + confidence per SNP site)
     t_call = time.perf_counter() - t0 - t_reads - t_reduce
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)

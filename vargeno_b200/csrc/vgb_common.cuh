@@ -90,6 +90,19 @@ __host__ __device__ __forceinline__ uint64_t ctx_digest(uint32_t list_id, uint32
 }
 
 #ifdef __CUDACC__
+// Loads of the index at RANDOM addresses.  A plain ld.global (with or without .nc) that misses L2 makes this part fetch
+// 128 bytes from DRAM -- four sectors for the one that is wanted (measured: tools/probes/sector_probe.cu under ncu,
+// profiles/r01_sector_probe.md); with the .L2::64B qualifier the same load moves 64 bytes.  There is no 32-byte variant.
+// Streaming reads (FASTQ text, line starts) keep the default: there the wider fetch is useful prefetch.
+#ifndef VGB_RANDOM_LOAD_QUAL
+#define VGB_RANDOM_LOAD_QUAL ".L2::64B"
+#endif
+__device__ __forceinline__ uint32_t ldr(const uint32_t *p) { uint32_t v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldr(const uint8_t *p) { uint32_t v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint64_t ldr(const uint64_t *p) { uint64_t v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint2 ldr(const uint2 *p) { uint2 v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ uint4 ldr(const uint4 *p) { uint4 v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+
 // BloomFilter::check_value, value_range 32 (src/generate_bf.h:112-114)
 __device__ __forceinline__ bool bf_ref(const DevIndex &ix, uint32_t lo32)
 {
@@ -97,7 +110,7 @@ __device__ __forceinline__ bool bf_ref(const DevIndex &ix, uint32_t lo32)
 	if (ix.ref_bf_bits <= 0xFFFFFFFFull) bit %= ix.ref_bf_bits;   // 9.6e9 bits in practice: the modulo is the identity
 	const uint64_t w = bit >> 5;
 	if (w >= ix.ref_bf_nw32) return false;
-	return (__ldg(ix.ref_bf + w) >> (bit & 31)) & 1u;
+	return (ldr(ix.ref_bf + w) >> (bit & 31)) & 1u;
 }
 // value_range 40 (src/generate_bf.h:115-116)
 __device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
@@ -105,26 +118,26 @@ __device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
 	const uint64_t bit = hash40(lo40) % ix.snp_bf_bits;
 	const uint64_t w = bit >> 5;
 	if (w >= ix.snp_bf_nw32) return false;
-	return (__ldg(ix.snp_bf + w) >> (bit & 31)) & 1u;
+	return (ldr(ix.snp_bf + w) >> (bit & 31)) & 1u;
 }
 
 // jumpgate pair of the HI32 block (src/qv.cc:219-233, check_block_size :242-264)
 __device__ __forceinline__ void ref_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
 	const uint64_t h = kmer >> 32;
-	lo = __ldg(ix.ref_jg + h);
-	hi = __ldg(ix.ref_jg + h + 1);
+	lo = ldr(ix.ref_jg + h);
+	hi = ldr(ix.ref_jg + h + 1);
 }
 __device__ __forceinline__ void ref_lo_bucket(const DevIndex &ix, uint32_t lo32, uint32_t &s, uint32_t &e)
 {
-	e = __ldg(ix.ref_jg_lo + lo32);
-	s = lo32 ? __ldg(ix.ref_jg_lo + lo32 - 1) : 0u;
+	e = ldr(ix.ref_jg_lo + lo32);
+	s = lo32 ? ldr(ix.ref_jg_lo + lo32 - 1) : 0u;
 }
 __device__ __forceinline__ void snp_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
 	const uint64_t h = kmer >> 40;
-	lo = __ldg(ix.snp_jg + h);
-	hi = __ldg(ix.snp_jg + h + 1);
+	lo = ldr(ix.snp_jg + h);
+	hi = ldr(ix.snp_jg + h + 1);
 }
 
 // query_ref_dict (src/qv.cc:206-240) inside an already known block: rank of the entry or -1
@@ -132,11 +145,11 @@ __device__ __forceinline__ int64_t ref_find_in_block(const DevIndex &ix, uint32_
 {
 	while (hi - lo > 4) {
 		const uint32_t mid = lo + ((hi - lo) >> 1);
-		const uint32_t v = __ldg(&ix.ref[mid].lo);
+		const uint32_t v = ldr(&ix.ref[mid].lo);
 		if (v <= key_lo) lo = mid; else hi = mid;
 	}
 	for (uint32_t i = lo; i < hi; i++) {
-		const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ix.ref + i));
+		const uint2 e = ldr(reinterpret_cast<const uint2 *>(ix.ref + i));
 		if (e.x == key_lo) { posx = e.y; return (int64_t)i; }
 	}
 	return -1;
@@ -155,11 +168,11 @@ __device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_
 	const uint64_t M40 = 0xFFFFFFFFFFull;
 	while (hi - lo > 2) {
 		const uint32_t mid = lo + ((hi - lo) >> 1);
-		const uint64_t v = __ldg(&ix.snp[mid].key) & M40;
+		const uint64_t v = ldr(&ix.snp[mid].key) & M40;
 		if (v <= key_lo40) lo = mid; else hi = mid;
 	}
 	for (uint32_t i = lo; i < hi; i++) {
-		const uint4 e = __ldg(reinterpret_cast<const uint4 *>(ix.snp + i));
+		const uint4 e = ldr(reinterpret_cast<const uint4 *>(ix.snp + i));
 		const uint64_t key = ((uint64_t)e.y << 32) | e.x;
 		if ((key & M40) == key_lo40) { out.key = key; out.pos = e.z; out.extra = e.w; return (int64_t)i; }
 	}
@@ -168,14 +181,14 @@ __device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_
 // LO40 of SNP entry (lo + 11 s): what step s of the reference's strided scan over the block starting at rank lo examines
 __device__ __forceinline__ uint64_t snp_scan_lo40(const DevIndex &ix, uint32_t lo, uint32_t s)
 {
-	return __ldg(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
+	return ldr(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
 }
 // block of the top 30 bits: only for exact membership (entry rank inside the HI24 block is not needed there)
 __device__ __forceinline__ void snp_block30(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
 	const uint64_t h = kmer >> 34;
-	lo = __ldg(ix.snp_jg30 + h);
-	hi = __ldg(ix.snp_jg30 + h + 1);
+	lo = ldr(ix.snp_jg30 + h);
+	hi = ldr(ix.snp_jg30 + h + 1);
 }
 __device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
 {
@@ -192,7 +205,7 @@ __device__ __forceinline__ uint32_t snp_flag_of(const SnpEntry &e) { return (uin
 __device__ __forceinline__ bool pile_nonzero(const DevIndex &ix, uint64_t p)
 {
 	if (p >= ix.pile_len) return false;
-	const uint64_t bits = __ldg(&ix.pile[p >> 6].bits);
+	const uint64_t bits = ldr(&ix.pile[p >> 6].bits);
 	return (bits >> (p & 63)) & 1ull;
 }
 

@@ -1,15 +1,17 @@
 // vgb_fastq.cu -- K1: FASTQ record framing on the device.
 //
 // Replaces the four fgets() per record of the reference (src/qv.cc:760-763): the raw text chunk is already in
-// HBM; three small kernels find every line start (newline count per 4 KiB tile -> exclusive scan -> scatter),
-// so the per-read kernel can address record r as lines 4r .. 4r+3 without any host parsing.
-// Streaming, 128-bit loads, bounded by HBM bandwidth (2 reads of the text + 4 B written per line).
+// HBM; one single-pass kernel finds every line start (newline masks per 64 KiB tile, decoupled look-back for the
+// running line number, scatter from registers), so the per-read kernel can address record r as lines 4r .. 4r+3
+// without any host parsing.  Streaming, 128-bit loads, bounded by HBM bandwidth (the text is read ONCE + 4 B written per line).
 #include "vgb_internal.h"
 
 namespace vgb {
 
-constexpr int FQ_T = 256;
-constexpr int FQ_TILE = FQ_T * 16;   // bytes per block
+constexpr int FQ_T = 512;
+constexpr int FQ_PER = 128;              // bytes per thread: eight 128-bit loads in flight
+constexpr int FQ_NV = FQ_PER / 16;
+constexpr int FQ_TILE = FQ_T * FQ_PER;   // 64 KiB per tile
 
 // 16-bit mask of '\n' positions among the 16 bytes at text[off .. off+16)
 __device__ __forceinline__ uint32_t nl_mask16(const char *text, uint64_t off, uint64_t n, bool aligned)
@@ -20,8 +22,10 @@ __device__ __forceinline__ uint32_t nl_mask16(const char *text, uint64_t off, ui
 		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const uint32_t eq = __vcmpeq4(w[k], 0x0A0A0A0Au);   // 0xFF in each matching byte
-			m |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * k);
+			// bytes equal to 0x0A -> bit 7 of the byte (exact zero-byte test on x = w ^ 0x0A0A0A0A), gathered by one multiply
+			const uint32_t x = w[k] ^ 0x0A0A0A0Au;
+			const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+			m |= (((z >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * k);
 		}
 	} else {
 		for (int k = 0; k < 16; k++)
@@ -30,17 +34,70 @@ __device__ __forceinline__ uint32_t nl_mask16(const char *text, uint64_t off, ui
 	return m;
 }
 
-__global__ void __launch_bounds__(FQ_T) k_fq_count(const char *text, uint64_t n, uint32_t *blk_counts)
+// One pass over the text: tiles are claimed in order through a counter, each tile counts its newlines, publishes the
+// count, learns how many newlines precede it by looking back over its predecessors' published values (decoupled
+// look-back, 32 predecessors per step), and writes its line starts straight from the masks it still holds in registers.
+// status[t] = flag << 32 | value: flag 0 = nothing yet, 1 = value is the tile's own count, 2 = value includes all before it.
+__global__ void __launch_bounds__(FQ_T) k_fq_index(const char *text, uint64_t n, uint32_t n_tiles, unsigned long long *status,
+                                                   uint32_t *tile_counter, uint32_t *total_nl, uint32_t *line_start, uint64_t line_cap)
 {
-	__shared__ uint32_t sm[FQ_T / 32];
-	const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-	const uint64_t off = (uint64_t)blockIdx.x * FQ_TILE + (uint64_t)threadIdx.x * 16;
-	uint32_t cnt = off < n ? __popc(nl_mask16(text, off, n, aligned)) : 0;
-#pragma unroll
-	for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-	if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+	__shared__ uint32_t s_tile, s_prefix, sm[FQ_T / 32];
+	if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
 	__syncthreads();
-	if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < FQ_T / 32; i++) t += sm[i]; blk_counts[blockIdx.x] = t; }
+	const uint32_t tile = s_tile;
+	const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
+	const uint64_t off = (uint64_t)tile * FQ_TILE + (uint64_t)threadIdx.x * FQ_PER;
+	uint32_t m[FQ_NV / 2];                 // two 16-bit masks per word
+	uint32_t cnt = 0;
+#pragma unroll
+	for (int k = 0; k < FQ_NV / 2; k++) {
+		const uint32_t lo = off + 32 * k < n ? nl_mask16(text, off + 32 * k, n, aligned) : 0;
+		const uint32_t hi = off + 32 * k + 16 < n ? nl_mask16(text, off + 32 * k + 16, n, aligned) : 0;
+		m[k] = lo | (hi << 16);
+		cnt += __popc(m[k]);
+	}
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = cnt;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) sm[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t v = lane < FQ_T / 32 ? sm[lane] : 0, vi = v;
+#pragma unroll
+		for (int o = 1; o < FQ_T / 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, vi, o); if (lane >= (uint32_t)o) vi += t; }
+		if (lane < FQ_T / 32) sm[lane] = vi - v;                       // exclusive prefix of the warp totals
+		const uint32_t total = __shfl_sync(0xffffffffu, vi, FQ_T / 32 - 1);
+		volatile unsigned long long *st = status;
+		if (lane == 0) st[tile] = ((tile == 0 ? 2ull : 1ull) << 32) | total;
+		uint32_t excl = 0;
+		if (tile > 0) {
+			int64_t base = (int64_t)tile - 1;
+			for (;;) {
+				const int64_t idx = base - lane;
+				unsigned long long sv = idx >= 0 ? st[idx] : (2ull << 32);   // in front of tile 0: nothing, final
+				while (__any_sync(0xffffffffu, (sv >> 32) == 0)) { if ((sv >> 32) == 0) sv = st[idx]; }
+				const uint32_t fin = __ballot_sync(0xffffffffu, (sv >> 32) == 2);
+				const uint32_t upto = fin ? (uint32_t)__ffs(fin) - 1 : 31u;   // nearest predecessor whose value is already a prefix
+				excl += __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)sv : 0u);
+				if (fin) break;
+				base -= 32;
+			}
+			if (lane == 0) st[tile] = (2ull << 32) | (excl + total);
+		}
+		if (lane == 0) { s_prefix = excl; if (tile == n_tiles - 1) *total_nl = excl + total; }
+	}
+	__syncthreads();
+	uint32_t idx = s_prefix + sm[w] + inc - cnt;               // newlines in front of this thread's bytes
+#pragma unroll
+	for (int k = 0; k < FQ_NV / 2; k++) {
+		uint32_t mm = m[k];
+		while (mm) {
+			const int b = __ffs(mm) - 1;
+			mm &= mm - 1;
+			if (++idx < line_cap) line_start[idx] = (uint32_t)(off + 32 * k + b + 1);   // line idx starts right after newline idx-1
+		}
+	}
 }
 
 // meta: [0] n_lines [1] n_reads [2] work counter [3] format error bits
@@ -59,42 +116,16 @@ __global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_
 	meta[5] |= err;                                        // sticky until vgb_reset_counts (the slot is reused by later chunks)
 }
 
-__global__ void __launch_bounds__(FQ_T) k_fq_scatter(const char *text, uint64_t n, const uint32_t *blk_excl, const uint32_t *meta, uint32_t *line_start)
+int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
 {
-	__shared__ uint32_t sm[FQ_T / 32 + 1];
-	if (meta[3] & 4) return;
-	const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-	const uint64_t off = (uint64_t)blockIdx.x * FQ_TILE + (uint64_t)threadIdx.x * 16;
-	const uint32_t m = off < n ? nl_mask16(text, off, n, aligned) : 0;
-	const uint32_t cnt = __popc(m);
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	uint32_t inc = cnt;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-	if (lane == 31) sm[w] = inc;
-	__syncthreads();
-	if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < FQ_T / 32; i++) { const uint32_t t = sm[i]; sm[i] = run; run += t; } }
-	__syncthreads();
-	uint32_t idx = blk_excl[blockIdx.x] + sm[w] + inc - cnt;   // global index of this thread's first newline
-	uint32_t mm = m;
-	while (mm) {
-		const int b = __ffs(mm) - 1;
-		mm &= mm - 1;
-		line_start[++idx] = (uint32_t)(off + b + 1);           // line idx starts right after newline idx-1
-	}
-}
-
-int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes)
-{
-	const uint64_t nblk = (nbytes + FQ_TILE - 1) / FQ_TILE;
+	const uint64_t n_tiles = (nbytes + FQ_TILE - 1) / FQ_TILE;
 	const uint64_t line_cap = c->max_chunk_bytes / 2 + 16;
-	uint32_t *tmp = ck.d_blk_counts + nblk + 8;                // scratch for the scan's tile sums
-	k_fq_count<<<(unsigned)nblk, FQ_T, 0, c->stream>>>(ck.d_text, nbytes, ck.d_blk_counts);
-	c->launches++;
-	int rc = exclusive_scan_u32(c, ck.d_blk_counts, ck.d_blk_counts, nblk, tmp, ck.d_meta + 4);
-	if (rc) return rc;
-	k_fq_finish<<<1, 1, 0, c->stream>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap);
-	k_fq_scatter<<<(unsigned)nblk, FQ_T, 0, c->stream>>>(ck.d_text, nbytes, ck.d_blk_counts, ck.d_meta, ck.d_line_start);
+	unsigned long long *status = reinterpret_cast<unsigned long long *>(ck.d_blk_counts);   // >= max_chunk_bytes / 512 bytes
+	VGB_CUDA(c, cudaMemsetAsync(status, 0, n_tiles * sizeof(unsigned long long), st));
+	VGB_CUDA(c, cudaMemsetAsync(ck.d_meta + 8, 0, sizeof(uint32_t), st));           // tile counter
+	k_fq_index<<<(unsigned)n_tiles, FQ_T, 0, st>>>(ck.d_text, nbytes, (uint32_t)n_tiles, status, ck.d_meta + 8, ck.d_meta + 4,
+	                                                     ck.d_line_start, line_cap);
+	k_fq_finish<<<1, 1, 0, st>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap);
 	c->launches += 2;
 	VGB_CUDA(c, cudaGetLastError());
 	return VGB_OK;

@@ -67,7 +67,7 @@ __device__ __forceinline__ void hit8(const DevIndex &ix, OctSmem *os, uint32_t l
 		const uint32_t p = __ldg(rowp + c);
 		if (p == 0) break;
 		bool veto = false;
-		if (d != NO_MOD) veto = list ? ((uint32_t)__ldg(ix.snp_aux_info + row + c) >> 3) == d : pile_nonzero(ix, (uint64_t)p + d);
+		if (d != NO_MOD) veto = list ? ((uint32_t)ldr(ix.snp_aux_info + row + c) >> 3) == d : pile_nonzero(ix, (uint64_t)p + d);
 		if (!veto) emit8(os, kmer, p, offset, d, kidx, list);
 	}
 }
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			bfr_bit = hash32((uint32_t)kmer);
 			if (ix.ref_bf_bits <= 0xFFFFFFFFull) bfr_bit %= ix.ref_bf_bits;
 			bfs_bit = hash40(kmer & 0xFFFFFFFFFFull) % ix.snp_bf_bits;
-			if ((bfr_bit >> 5) < ix.ref_bf_nw32) bfr_w = __ldg(ix.ref_bf + (bfr_bit >> 5));
-			if ((bfs_bit >> 5) < ix.snp_bf_nw32) bfs_w = __ldg(ix.snp_bf + (bfs_bit >> 5));
+			if ((bfr_bit >> 5) < ix.ref_bf_nw32) bfr_w = ldr(ix.ref_bf + (bfr_bit >> 5));
+			if ((bfs_bit >> 5) < ix.snp_bf_nw32) bfs_w = ldr(ix.snp_bf + (bfs_bit >> 5));
 			ref_lo_bucket(ix, (uint32_t)kmer, bs, be);     // speculative: used only if the ref Bloom gate is open
 		}
 		// ---- level 2: exact entries (src/qv.cc:840-937) ----
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				uint32_t list = 0, v = 0, fi = 0, d = 0;
 				uint64_t nb = 0;
 				if (t < e0) {                                     // LO32 bucket entry
-					const uint2 en = __ldg(reinterpret_cast<const uint2 *>(ix.ref_by_lo + k_bs + t));
+					const uint2 en = ldr(reinterpret_cast<const uint2 *>(ix.ref_by_lo + k_bs + t));
 					const int sl = one_base_slot((uint64_t)(en.x ^ (uint32_t)(km >> 32)));
 					if (sl >= 0) { hit = true; nb = ((uint64_t)en.x << 32) | (uint32_t)km; v = en.y; d = 16u + (uint32_t)sl; }
 				} else if (t < e2 || (k_big && t >= e3)) {        // snp query
@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					const uint32_t s = t - e2;
 					const uint64_t ex = (uint64_t)k_rlo + (uint64_t)REF_STRIDE * s;
 					if (ex < ix.n_ref) {
-						const uint32_t entry_lo = __ldg(&ix.ref[ex].lo);
+						const uint32_t entry_lo = ldr(&ix.ref[ex].lo);
 						const int dd = one_base_slot((uint64_t)((uint32_t)km ^ entry_lo));
-						if (dd >= 0) { hit = true; nb = (km & 0xFFFFFFFF00000000ull) | entry_lo; v = __ldg(&ix.ref[k_rlo + s].posx); d = (uint32_t)dd; }
+						if (dd >= 0) { hit = true; nb = (km & 0xFFFFFFFF00000000ull) | entry_lo; v = ldr(&ix.ref[k_rlo + s].posx); d = (uint32_t)dd; }
 					}
 				} else {                                          // snp strided scan step (F13)
 					const uint32_t s = t - e3;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						const uint64_t entry_lo = snp_scan_lo40(ix, k_slo, s);
 						const int dd = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
 						if (dd >= 0) {
-							const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ix.snp + k_slo + s));
+							const uint4 raw = ldr(reinterpret_cast<const uint4 *>(ix.snp + k_slo + s));
 							hit = true; list = 1; nb = (km & 0xFFFFFF0000000000ull) | entry_lo; v = raw.z; fi = (raw.y >> 8) & 0xFFFFu; d = (uint32_t)dd;
 						}
 					}
@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				// the 32-position window [kpos, kpos+32) lies in one or two 64-position blocks of the site bitmap
 				const uint64_t bA = kpos >> 6, bB = (kpos + 31) >> 6;
 				uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
-				if (bA < n_blk) ka = __ldg(reinterpret_cast<const uint4 *>(ix.pile + bA));
-				if (bB != bA && bB < n_blk) kb = __ldg(reinterpret_cast<const uint4 *>(ix.pile + bB));
+				if (bA < n_blk) ka = ldr(reinterpret_cast<const uint4 *>(ix.pile + bA));
+				if (bB != bA && bB < n_blk) kb = ldr(reinterpret_cast<const uint4 *>(ix.pile + bB));
 				const uint64_t bitsA = ((uint64_t)ka.y << 32) | ka.x, bitsB = ((uint64_t)kb.y << 32) | kb.x;
 				const uint32_t sh = (uint32_t)(kpos & 63);
 				uint32_t win = (uint32_t)(bitsA >> sh);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					const uint32_t off = sh + b;                    // bit index relative to block A
 					const uint32_t sid = off < 64 ? ka.z + __popcll(bitsA & ((1ull << off) - 1))
 					                              : kb.z + __popcll(bitsB & ((1ull << (off - 64)) - 1));
-					const uint32_t code = __ldg(ix.site_code + sid);
+					const uint32_t code = ldr(ix.site_code + sid);
 					const uint32_t rbase = code & 3, abase = code >> 2;
 					if (rbase == abase) continue;                  // p->ref != p->alt (:1404)
 					const uint32_t base = (uint32_t)(kmer_e >> (2 * b)) & 3u;

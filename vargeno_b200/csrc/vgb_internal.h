@@ -24,7 +24,7 @@ struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i
 	uint32_t *d_blk_counts = nullptr; // newline count per 4 KiB tile, then its exclusive scan
 	uint32_t *d_defer = nullptr;      // read indices the 8-lane kernel hands to the warp-per-read kernel
 	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter
-	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr;
+	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, g0 = nullptr;
 	bool busy = false;
 };
 
@@ -34,7 +34,7 @@ struct vgb_ctx {
 	vgb_config cfg{};
 	int device = 0;
 	int sm_count = 148;
-	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;   // kernels | H2D copies (chunk i+1 is copied under the kernels of chunk i)
 	std::string err;
 
 	// index (device)
@@ -96,7 +96,7 @@ int dev_alloc(vgb_ctx *c, T **p, uint64_t count, bool own = true)
 // vgb_index.cu
 int index_upload(vgb_ctx *c, const vgb_index_view *v);
 // vgb_fastq.cu
-int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes);
+int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st);
 // vgb_geno.cu
 int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id);
 int geno_prepare(vgb_ctx *c);

@@ -186,8 +186,10 @@ class Genotyper:
         self._ck(self.L.vgb_fetch_pileup(self.h, _lib.ptr(r), _lib.ptr(a), self.n_sites))
         return r, a
 
-    def call(self) -> Tuple[np.ndarray, np.ndarray]:
-        g, c = np.zeros(self.n_sites, "u1"), np.zeros(self.n_sites, "<f8")
+    def call(self, out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """GT code + confidence per site.  `out`: caller-owned (e.g. pinned) uint8 / float64 arrays of n_sites elements."""
+        g, c = out if out is not None else (np.zeros(self.n_sites, "u1"), np.zeros(self.n_sites, "<f8"))
+        assert g.dtype == np.uint8 and c.dtype == np.float64 and g.size == self.n_sites and c.size == self.n_sites
         self._ck(self.L.vgb_call(self.h, _lib.ptr(g), _lib.ptr(c), self.n_sites))
         return g, c
 
