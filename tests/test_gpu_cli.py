@@ -48,3 +48,41 @@ def test_cli_rejects_bad_usage(tmp_path):
     vb.build()
     p = subprocess.run([vb.HOST_BIN, "geno", "only", "three", "args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode != 0
+
+
+def _sha(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 24), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", ["s0", "advA", "advB"])
+def test_cli_index_files_are_byte_identical(cache, name, tmp_path):
+    """`vargeno-b200 index` (text parsing on the host, sort / collapse / Bloom filters on the GPU) must write the five files the
+    compiled reference's `vargeno index` wrote: sizes and sha256 from tests/golden/<name>.json."""
+    import json
+    vb.build()
+    man = json.load(open(os.path.join(GOLD, name + ".json")))
+    ds = cache.dataset(name)
+    prefix = str(tmp_path / "cli")
+    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix, "--verbose"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    for ext in ("ref.dict", "snp.dict", "ref.bf", "snp.bf", "chrlens"):
+        assert os.path.getsize(prefix + "." + ext) == man["index_bytes"][ext], ext
+        assert _sha(prefix + "." + ext) == man["index"][ext], ext
+
+
+def test_cli_index_then_geno(cache, tmp_path):
+    """The two commands back to back, as a user of the reference would run them."""
+    vb.build()
+    ds = cache.dataset("s0")
+    prefix = str(tmp_path / "ix")
+    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    out = str(tmp_path / "out.vcf")
+    p = subprocess.run([vb.HOST_BIN, "geno", prefix, ds.fastq, ds.vcf, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "s0.out.vcf"), "rb").read()

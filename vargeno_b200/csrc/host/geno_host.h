@@ -51,4 +51,9 @@ int rewrite_vcf(const std::string &vcf_in, const std::string &vcf_out, const std
 int run_geno(const std::string &prefix, const std::string &fastq, const std::string &vcf_in, const std::string &vcf_out,
              int n_gpus, uint64_t chunk_bytes, bool verbose);
 
+// the whole `index` command: FASTA + VCF text -> device builder -> the five index files (index_host.cpp)
+// dump_parse: write the parsed contigs / SNP lines as text to that file and stop before the device step (host-logic tests)
+int run_index(const std::string &fasta, const std::string &vcf, const std::string &prefix, int device, bool verbose,
+              const std::string &dump_parse = std::string());
+
 }  // namespace vgh

@@ -1,5 +1,6 @@
 // vargeno_main.cpp -- `vargeno-b200`: the reference's command line (src/qv.cc:1853-1881, 2109-2131) in front of the
-// B200 hot path.  `geno` is the drop-in; `index` stays with the reference program (the on-disk index is unchanged).
+// B200 hot path.  `geno` is the drop-in for the hot path; `index` writes the same five files as the reference's
+// `vargeno index` (byte-identical), with the sort / collapse / Bloom-filter work done on the GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,8 +15,8 @@ static void print_help()
 	fprintf(stderr, "------  -----------                   ----------\n");
 	fprintf(stderr, "geno    Perform genotyping (B200)     <index_prefix> <input FASTQ> <input SNPs in VCF> <output file in VCF> "
 	                "[--gpus N] [--chunk-mb M] [--verbose]\n");
-	fprintf(stderr, "index   not re-implemented: run the reference's `vargeno index <input FASTA> <input SNPs in VCF> <index_prefix>`;\n");
-	fprintf(stderr, "        its five files are read unchanged\n");
+	fprintf(stderr, "index   Build the index (B200)         <input FASTA> <input SNPs in VCF> <index_prefix> [--gpu D] [--verbose]\n");
+	fprintf(stderr, "        (same five files as the reference's `vargeno index`, byte for byte)\n");
 }
 
 int main(int argc, const char *argv[])
@@ -36,6 +37,20 @@ int main(int argc, const char *argv[])
 		}
 		if (npos != 4 || gpus < 1 || chunk_mb < 1 || chunk_mb > 4000) { print_help(); return EXIT_FAILURE; }   // arg_check, src/qv.cc:1875-1881
 		return vgh::run_geno(pos[0], pos[1], pos[2], pos[3], gpus, chunk_mb << 20, verbose);
+	}
+	if (opt == "index") {
+		std::string pos[3], dump;
+		int npos = 0, dev = 0;
+		bool verbose = false;
+		for (int i = 2; i < argc; i++) {
+			if (!strcmp(argv[i], "--gpu") && i + 1 < argc) dev = atoi(argv[++i]);
+			else if (!strcmp(argv[i], "--dump-parse") && i + 1 < argc) dump = argv[++i];
+			else if (!strcmp(argv[i], "--verbose")) verbose = true;
+			else if (npos < 3) pos[npos++] = argv[i];
+			else npos++;
+		}
+		if (npos != 3 || dev < 0) { print_help(); return EXIT_FAILURE; }   // arg_check, src/qv.cc:1875-1881
+		return vgh::run_index(pos[0], pos[1], pos[2], dev, verbose, dump);
 	}
 	if (opt == "help") { print_help(); return EXIT_SUCCESS; }
 	print_help();

@@ -4,14 +4,13 @@
 // HBM; one single-pass kernel finds every line start (newline masks per 64 KiB tile, decoupled look-back for the
 // running line number, scatter from registers), so the per-read kernel can address record r as lines 4r .. 4r+3
 // without any host parsing.  Streaming, 128-bit loads, bounded by HBM bandwidth (the text is read ONCE + 4 B written per line).
+#include <cstdlib>
+
 #include "vgb_internal.h"
 
 namespace vgb {
 
-constexpr int FQ_T = 512;
-constexpr int FQ_PER = 128;              // bytes per thread: eight 128-bit loads in flight
-constexpr int FQ_NV = FQ_PER / 16;
-constexpr int FQ_TILE = FQ_T * FQ_PER;   // 64 KiB per tile
+// tile = FQ_T threads x FQ_PER bytes each (FQ_PER / 16 independent 128-bit loads per thread); default 256 x 256 B = 64 KiB
 
 // 16-bit mask of '\n' positions among the 16 bytes at text[off .. off+16)
 __device__ __forceinline__ uint32_t nl_mask16(const char *text, uint64_t off, uint64_t n, bool aligned)
@@ -38,9 +37,12 @@ __device__ __forceinline__ uint32_t nl_mask16(const char *text, uint64_t off, ui
 // count, learns how many newlines precede it by looking back over its predecessors' published values (decoupled
 // look-back, 32 predecessors per step), and writes its line starts straight from the masks it still holds in registers.
 // status[t] = flag << 32 | value: flag 0 = nothing yet, 1 = value is the tile's own count, 2 = value includes all before it.
+template <int FQ_T, int FQ_PER>
 __global__ void __launch_bounds__(FQ_T) k_fq_index(const char *text, uint64_t n, uint32_t n_tiles, unsigned long long *status,
                                                    uint32_t *tile_counter, uint32_t *total_nl, uint32_t *line_start, uint64_t line_cap)
 {
+	constexpr int FQ_NV = FQ_PER / 16;
+	constexpr int FQ_TILE = FQ_T * FQ_PER;
 	__shared__ uint32_t s_tile, s_prefix, sm[FQ_T / 32];
 	if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
 	__syncthreads();
@@ -116,15 +118,28 @@ __global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_
 	meta[5] |= err;                                        // sticky until vgb_reset_counts (the slot is reused by later chunks)
 }
 
+template <int T, int PER>
+static void launch_fq_index(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t line_cap, cudaStream_t st)
+{
+	const uint64_t n_tiles = (nbytes + (uint64_t)T * PER - 1) / ((uint64_t)T * PER);
+	unsigned long long *status = reinterpret_cast<unsigned long long *>(ck.d_blk_counts);   // >= max_chunk_bytes / 512 bytes
+	cudaMemsetAsync(status, 0, n_tiles * sizeof(unsigned long long), st);
+	cudaMemsetAsync(ck.d_meta + 8, 0, sizeof(uint32_t), st);                               // tile counter
+	k_fq_index<T, PER><<<(unsigned)n_tiles, T, 0, st>>>(ck.d_text, nbytes, (uint32_t)n_tiles, status, ck.d_meta + 8, ck.d_meta + 4,
+	                                                   ck.d_line_start, line_cap);
+}
+
 int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
 {
-	const uint64_t n_tiles = (nbytes + FQ_TILE - 1) / FQ_TILE;
 	const uint64_t line_cap = c->max_chunk_bytes / 2 + 16;
-	unsigned long long *status = reinterpret_cast<unsigned long long *>(ck.d_blk_counts);   // >= max_chunk_bytes / 512 bytes
-	VGB_CUDA(c, cudaMemsetAsync(status, 0, n_tiles * sizeof(unsigned long long), st));
-	VGB_CUDA(c, cudaMemsetAsync(ck.d_meta + 8, 0, sizeof(uint32_t), st));           // tile counter
-	k_fq_index<<<(unsigned)n_tiles, FQ_T, 0, st>>>(ck.d_text, nbytes, (uint32_t)n_tiles, status, ck.d_meta + 8, ck.d_meta + 4,
-	                                                     ck.d_line_start, line_cap);
+	const int variant = getenv("VGB_FQ_VARIANT") ? atoi(getenv("VGB_FQ_VARIANT")) : 0;   // tuning aid (tools/perf_sweep.py)
+	// measured on B200, 632 MB of FASTQ (profiles/r01_summary.md): 256 x 256 B 0.225 ms, 128 x 256 B 0.235, 512 x 128 B 0.262,
+	// 256 x 128 B 0.267, 128 x 128 B 0.281, 1024 x 64 B 0.293 -- bytes in flight per thread matter more than the tile size
+	switch (variant) {
+	case 1: launch_fq_index<512, 128>(c, ck, nbytes, line_cap, st); break;
+	case 2: launch_fq_index<256, 512>(c, ck, nbytes, line_cap, st); break;
+	default: launch_fq_index<256, 256>(c, ck, nbytes, line_cap, st); break;
+	}
 	k_fq_finish<<<1, 1, 0, st>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap);
 	c->launches += 2;
 	VGB_CUDA(c, cudaGetLastError());
