@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 REC_ID_WIDTH = 9
+# DRAM bytes one k_geno8 launch really moves (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
+# this workload at 2 M reads per launch: profiles/r01_k_geno8_ncu_full.csv); a number taken under the profiler, so it is a
+# constant here, not something measured in the timed run
+NCU_TRAFFIC = {"bytes": 3.516052e9 + 58.842368e6, "reads_per_launch": 2_000_000, "source": "profiles/r01_k_geno8_ncu_full.csv"}
 S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS = 0.005, 0.25, 4
 
 
@@ -252,7 +256,9 @@ def run_ours(args):
             "kmer_lookups_per_s": d_lookups * world / dt if world == 1 else None,
             "lookups_per_read": d_lookups / max(1, st1["reads"] - st0["reads"]),
             "placed_fraction": (st1["placed"] - st0["placed"]) / max(1, st1["reads"] - st0["reads"]),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC["bytes"] * B / NCU_TRAFFIC["reads_per_launch"] if args.scale == 1.0 else None,
+                         "traffic_source": NCU_TRAFFIC["source"],
                          "kernel": "k_geno8 (+ list-mode k_geno for deferred reads)", "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": d_ms_geno / K,
                          "peak_source": peak_src, "note": "32 B (one DRAM sector) per dictionary lookup, SURVEY.md 8(d)",
                          "random_sector_peak_gbs": rs, "frac_of_random_sector_peak": (achieved / rs) if rs else None},

@@ -86,3 +86,31 @@ def test_cli_index_then_geno(cache, tmp_path):
     p = subprocess.run([vb.HOST_BIN, "geno", prefix, ds.fastq, ds.vcf, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 0, p.stderr
     assert open(out, "rb").read() == open(os.path.join(GOLD, "s0.out.vcf"), "rb").read()
+
+
+def test_cli_gzip_and_split_fastq(cache, tmp_path):
+    """gzip input and a comma-separated list of files read back to back (mates of a paired run are concatenated
+    for the reference, experiment/experiment.md:22-27).  The split is NOT at a record boundary and one half is gzip: the VCF
+    must still be the reference's, byte for byte."""
+    import gzip
+    vb.build()
+    ds = cache.dataset("advA")
+    prefix = str(tmp_path / "ix")
+    ib.write_index(cache.index("advA"), prefix)
+    text = open(ds.fastq, "rb").read()
+    cut = len(text) // 2 + 17
+    a, b = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq")
+    with gzip.open(a, "wb", compresslevel=1) as f:
+        f.write(text[:cut])
+    open(b, "wb").write(text[cut:])
+    out = str(tmp_path / "out.vcf")
+    p = subprocess.run([vb.HOST_BIN, "geno", prefix, a + "," + b, ds.vcf, out, "--chunk-mb", "1"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "advA.out.vcf"), "rb").read()
+    whole = str(tmp_path / "whole.fq.gz")
+    with gzip.open(whole, "wb", compresslevel=1) as f:
+        f.write(text)
+    p = subprocess.run([vb.HOST_BIN, "geno", prefix, whole, ds.vcf, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "advA.out.vcf"), "rb").read()

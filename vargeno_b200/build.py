@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if all(os.path.exists(s) for s in host_srcs):
         if force or _newer(HOST_BIN, host_srcs + hdrs + [LIB]):
             _run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", HOST_BIN] + host_srcs +
-                 ["-L" + HERE, "-lvgb200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+                 ["-L" + HERE, "-lvgb200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz"])
     return LIB
 
 

@@ -5,7 +5,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -105,11 +107,73 @@ static uint64_t count_newlines(const char *p, uint64_t n)
 	return c;
 }
 
+// FASTQ byte source: one file or a comma-separated list read back to back (what `cat a.fq b.fq` would feed the reference:
+// experiment/experiment.md:22-27 concatenates the mates of a paired run), each file plain or gzip (magic 1f 8b, inflated
+// on the host with zlib -- SURVEY 8(f)-3).  Plain files are read() straight into the pinned chunk buffer.
+namespace {
+struct FastqSource {
+	std::vector<std::string> paths;
+	size_t next = 0;
+	int fd = -1;
+	gzFile gz = nullptr;
+	bool open_next(std::string &err)
+	{
+		close_cur();
+		if (next >= paths.size()) return false;
+		const std::string &p = paths[next++];
+		fd = ::open(p.c_str(), O_RDONLY);
+		if (fd < 0) { err = "cannot open " + p; return false; }
+		posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+		unsigned char magic[2] = { 0, 0 };
+		const ssize_t got = ::pread(fd, magic, 2, 0);
+		if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+			gz = gzdopen(fd, "rb");                     // takes the descriptor over
+			if (!gz) { err = "cannot inflate " + p; ::close(fd); fd = -1; return false; }
+			gzbuffer(gz, 1u << 20);
+			fd = -1;
+		}
+		return true;
+	}
+	void close_cur()
+	{
+		if (gz) gzclose(gz);
+		if (fd >= 0) ::close(fd);
+		gz = nullptr; fd = -1;
+	}
+	// up to n bytes into buf; 0 = end of all input, < 0 = error (err filled)
+	int64_t read(char *buf, uint64_t n, std::string &err)
+	{
+		for (;;) {
+			if (fd < 0 && !gz) {
+				if (next >= paths.size()) return 0;
+				if (!open_next(err)) return -1;
+			}
+			int64_t got;
+			if (gz) {
+				got = gzread(gz, buf, (unsigned)std::min<uint64_t>(n, 1u << 30));
+				if (got < 0) { int e = 0; err = std::string("gzip error in ") + paths[next - 1] + ": " + gzerror(gz, &e); return -1; }
+			} else {
+				got = ::read(fd, buf, n);
+				if (got < 0) { err = "read error on " + paths[next - 1]; return -1; }
+			}
+			if (got > 0) return got;
+			close_cur();                                // end of this file: go on with the next one
+		}
+	}
+	~FastqSource() { close_cur(); }
+};
+}  // namespace
+
 int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
 {
-	const int fd = ::open(path.c_str(), O_RDONLY);
-	if (fd < 0) { err = "cannot open " + path; return VGB_E_ARG; }
-	posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+	FastqSource src;
+	{
+		size_t a = 0, b;
+		while ((b = path.find(',', a)) != std::string::npos) { if (b > a) src.paths.push_back(path.substr(a, b - a)); a = b + 1; }
+		if (a < path.size()) src.paths.push_back(path.substr(a));
+	}
+	if (src.paths.empty()) { err = "no FASTQ file given"; return VGB_E_ARG; }
+	if (!src.open_next(err)) return VGB_E_ARG;
 	std::vector<char> carry;                                    // bytes of the record cut at the end of the previous chunk
 	uint64_t read_id = 0;
 	n_chunks = 0;
@@ -129,8 +193,8 @@ int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, ui
 		memcpy(buf, carry.data(), have);
 		carry.clear();
 		while (!eof && have < cap) {
-			const ssize_t got = ::read(fd, buf + have, cap - have);
-			if (got < 0) { err = "read error on " + path; rc = VGB_E_ARG; break; }
+			const int64_t got = src.read(buf + have, cap - have, err);
+			if (got < 0) { rc = VGB_E_ARG; break; }
 			if (got == 0) { eof = true; break; }
 			have += (uint64_t)got;
 		}
@@ -155,7 +219,6 @@ int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, ui
 		read_id += lines / 4;
 		n_chunks++;
 	}
-	::close(fd);
 	return rc;
 }
 

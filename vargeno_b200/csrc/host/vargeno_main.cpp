@@ -15,6 +15,7 @@ static void print_help()
 	fprintf(stderr, "------  -----------                   ----------\n");
 	fprintf(stderr, "geno    Perform genotyping (B200)     <index_prefix> <input FASTQ> <input SNPs in VCF> <output file in VCF> "
 	                "[--gpus N] [--chunk-mb M] [--verbose]\n");
+	fprintf(stderr, "        (<input FASTQ>: one file or a comma-separated list read back to back; each plain or gzip)\n");
 	fprintf(stderr, "index   Build the index (B200)         <input FASTA> <input SNPs in VCF> <index_prefix> [--gpu D] [--verbose]\n");
 	fprintf(stderr, "        (same five files as the reference's `vargeno index`, byte for byte)\n");
 }

@@ -119,9 +119,8 @@ __global__ void __launch_bounds__(256) k_random_sectors(const uint4 *buf, uint64
 		uint4 v[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			s = s * 6364136223846793005ull + 1442695040888963407ull;
-			const uint64_t sec = __umul64hi(s ^ (s >> 29), n_sectors);
-			v[k] = __ldg(buf + 2 * sec);
+			s = mix64(s + k + 1);                      // same generator as tools/probes/sector_probe.cu (an LCG here measured ~25 % low)
+			v[k] = __ldg(buf + 2 * (s % n_sectors));
 		}
 #pragma unroll
 		for (int k = 0; k < 8; k++) acc += v[k].x ^ v[k].w;

@@ -54,11 +54,14 @@ __global__ void __launch_bounds__(256) k_probe(const uint4 *buf, uint64_t n_sect
 	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
+static unsigned g_grid = 148 * 64;
+static uint32_t g_per_thread = 64;
+
 template <int MODE>
 static void run(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink)
 {
-	const uint32_t per_thread = 64;
-	const unsigned grid = 148 * 64;
+	const uint32_t per_thread = g_per_thread;
+	const unsigned grid = g_grid;
 	const uint64_t loads = (uint64_t)grid * 256 * per_thread;
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -70,7 +73,7 @@ static void run(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned
 	float ms = 0;
 	cudaEventElapsedTime(&ms, e0, e1);
 	ms /= 3;
-	printf("{\"flavour\": \"%s\", \"ms\": %.3f, \"loads_per_s\": %.4g, \"useful_gbs_at_32B\": %.1f, \"err\": \"%s\"}\n", name, ms, loads / (ms * 1e-3),
+	printf("{\"flavour\": \"%s\", \"grid\": %u, \"per_thread\": %u, \"ms\": %.3f, \"loads_per_s\": %.4g, \"useful_gbs_at_32B\": %.1f, \"err\": \"%s\"}\n", name, grid, per_thread, ms, loads / (ms * 1e-3),
 	       loads * 32.0 / (ms * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
 	fflush(stdout);
 }
@@ -79,6 +82,8 @@ int main(int argc, char **argv)
 {
 	const uint64_t gib = argc > 1 ? strtoull(argv[1], nullptr, 10) : 32;
 	const int gran = argc > 2 ? atoi(argv[2]) : 0;
+	if (argc > 4) g_grid = (unsigned)atoi(argv[4]);          // CTAs of 256 threads
+	if (argc > 5) g_per_thread = (uint32_t)atoi(argv[5]);    // loads per thread (multiple of 8)
 	if (gran) {
 		cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
 		size_t got = 0;
