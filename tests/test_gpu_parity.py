@@ -233,6 +233,11 @@ def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
     for k in ("reads", "passes", "placed", "exact_lookups", "nbr_query_lookups", "nbr_scan_reads", "events", "pileup_incr", "big_kmers"):
         assert st[k] == ost[k], k
     assert int(want["n_ref"].max()) + int(want["n_snp"].max()) > 24, "the set should contain reads beyond the shared-memory context budget"
+    # short reads (<= 8 k-mers) whose RETRY pass overflows the budget: the 8-lane kernel has already run and accounted for their
+    # forward pass and hands over only the retry (bit 31 of the deferred-list entry)
+    short = np.arange(want.size) >= 1900
+    n_retry_overflow = int(np.count_nonzero(short & (want["passes"] == 2) & (want["n_ref"].astype(int) + want["n_snp"].astype(int) > 24)))
+    assert n_retry_overflow > 0, "the set should contain short reads that overflow in the retry pass"
     o.close()
     # the warp-per-read kernel alone gives the same answer
     os.environ["VGB_GENO_KERNEL"] = "warp"
