@@ -126,11 +126,16 @@ def make_adv_a(d: str) -> Dataset:
     return _write(d, "advA", g, snps, parts, extra_lines=extra)
 
 
-def make_adv_b(d: str) -> Dataset:
+def adv_b_genome():
+    """The advB genome with its bookkeeping (repeat copies, motif sites): a pure function of its seeds."""
     motif = b"ACGGTCATGCAAGTCC"
     fams = [(300, 12, 0, 1), (500, 14, 0, 2), (250, 6, 0, 3), (180, 3, 1, 4), (90, 11, 0, 5)]
-    g = synth.make_genome([("chr7", 400000)], seed=23, n_runs=[(0, 170000, 64)], repeats=fams,
-                          motifs=[(motif, 160), (b"T" * 16, 30), (b"T" * 40, 6), (b"A" * 40, 4)])
+    return synth.make_genome([("chr7", 400000)], seed=23, n_runs=[(0, 170000, 64)], repeats=fams,
+                             motifs=[(motif, 160), (b"T" * 16, 30), (b"T" * 40, 6), (b"A" * 40, 4)])
+
+
+def make_adv_b(d: str) -> Dataset:
+    g = adv_b_genome()
     base = synth.make_snps(g, 400, seed=23, cluster_frac=0.25)
     rows = _rows(base)
     _snps_in_repeats(g, 23, [1, 2, 3, 4, 5], 3, rows)

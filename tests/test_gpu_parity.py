@@ -214,6 +214,15 @@ def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
     for L, n in ((288, 600), (320, 600), (650, 400), (1000, 300), (150, 800), (100, 400)):
         parts.append(synth.simulate_reads(g0, haps, n, L, seed=77 + L, sub_rate=0.01, lowq_prob=0.7, lowq_chars=31, first_id=first))
         first += n
+    # reverse-strand 150 bp reads over the 6-copy repeat family, all leading qualities low: the forward pass finds nothing, the
+    # retry finds 6 positions per k-mer (24 exact contexts) plus neighbours -> more than the 8-lane kernel keeps
+    gb = datasets.adv_b_genome()
+    rs = np.array([o + d for (_, _, ci, o, l) in gb.repeat_copies if l == 250 for d in (0, 7, 33, 64, 100)] * 4, dtype=np.int64)
+    assert rs.size >= 100
+    n_before_retry_set = first
+    parts.append(synth.simulate_reads(gb, (gb.concat(), gb.concat()), rs.size, 150, seed=91, sub_rate=0.002, lowq_prob=1.0, lowq_chars=4,
+                                      first_id=first, forced_starts=rs, forced_rev=np.ones(rs.size, bool)))
+    first += rs.size
     fq = np.concatenate(parts)
     o = orc.Oracle(ix)
     want = o.process_fastq(fq)
@@ -235,7 +244,7 @@ def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
     assert int(want["n_ref"].max()) + int(want["n_snp"].max()) > 24, "the set should contain reads beyond the shared-memory context budget"
     # short reads (<= 8 k-mers) whose RETRY pass overflows the budget: the 8-lane kernel has already run and accounted for their
     # forward pass and hands over only the retry (bit 31 of the deferred-list entry)
-    short = np.arange(want.size) >= 1900
+    short = np.arange(want.size) >= n_before_retry_set
     n_retry_overflow = int(np.count_nonzero(short & (want["passes"] == 2) & (want["n_ref"].astype(int) + want["n_snp"].astype(int) > 24)))
     assert n_retry_overflow > 0, "the set should contain short reads that overflow in the retry pass"
     o.close()
