@@ -114,7 +114,7 @@ __global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_
 		if (open_tail) { line_start[lines + 1] = (uint32_t)(n + 1); lines += 1; }
 	}
 	if (lines % 4) err |= 1;                               // truncated record (the reference would reuse stale buffers)
-	meta[0] = lines; meta[1] = lines / 4; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0;
+	meta[0] = lines; meta[1] = lines / 4; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0; meta[9] = 0; meta[10] = 0;
 	meta[5] |= err;                                        // sticky until vgb_reset_counts (the slot is reused by later chunks)
 }
 

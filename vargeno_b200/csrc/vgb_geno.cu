@@ -48,7 +48,9 @@ struct GenoArgs {
 	vgb_read_result *trace;       // nullptr unless VGB_CFG_TRACE
 	Event *spill;                 // [grid warps][EV_CAP - EV_SMEM]
 	const uint32_t *list;         // warp kernel: nullptr = every read of the chunk, else the deferred reads (count in meta[6])
-	uint32_t *defer;              // 8-lane kernel: where deferred read indices go
+	uint32_t *defer;              // group kernels: where read indices for the warp kernel go (bit 31: start at the retry pass)
+	const uint32_t *klist;        // 8-lane kernel behind the 4-lane one: the reads it was handed (count in meta[9]); nullptr = whole chunk
+	uint32_t *kdefer;             // 4-lane kernel: reads with 5..8 k-mers, for the 8-lane kernel
 };
 
 struct LaneStats {
@@ -491,37 +493,51 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 #include "vgb_geno8.inl"
 
 typedef void (*geno_kernel_t)(const GenoArgs);
-static geno_kernel_t g_warp_kernel = nullptr, g_oct_kernel = nullptr, g_oct_kernel_trace = nullptr;
-static size_t oct_smem_bytes() { return sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t) + sizeof(Pend) * GW * PEND_CAP; }
-static uint32_t g_oct_grid = 0;
+static geno_kernel_t g_warp_kernel = nullptr;
+static geno_kernel_t g_grp_kernel[2][2] = {};        // [lanes per read: 0 = 4, 1 = 8][trace]
+static uint32_t g_grp_grid[2] = {};
+static bool g_use_quad = true;
+static size_t grp_smem_bytes(int G) { const size_t R = 32 / G; return sizeof(OctSmem) * GW * R + GW * 16 * sizeof(uint32_t) + (G == 4 ? sizeof(Pend<4>) : sizeof(Pend<8>)) * GW * 2 * R; }
+
+template <int G>
+static void pick_group_kernels(int minb, geno_kernel_t &k, geno_kernel_t &kt)
+{
+	if (minb >= 6) { k = k_geno8<6, false, G>; kt = k_geno8<6, true, G>; }
+	else if (minb == 5) { k = k_geno8<5, false, G>; kt = k_geno8<5, true, G>; }
+	else if (minb == 3) { k = k_geno8<3, false, G>; kt = k_geno8<3, true, G>; }
+	else { k = k_geno8<4, false, G>; kt = k_geno8<4, true, G>; }
+}
 
 int geno_prepare(vgb_ctx *c)
 {
-	// VGB_GENO_KERNEL=warp: one warp per read for everything (the first version, kept as the path for deferred reads)
-	// VGB_GENO_MINB / VGB_GENO8_MINB: register budget variants (CTAs per SM the compiler must make room for)
-	int minb = 4, minb8 = 4;     // measured on B200 (profiles/r01_summary.md): 62 registers, no spills, 32 warps per SM beats 40 registers / 48 warps
+	// VGB_GENO_KERNEL=warp: one warp per read for everything (the first version, kept as the path for deferred reads);
+	//                =oct:  no 4-lane kernel in front (reads of 129..287 bases dominate)
+	// VGB_GENO_MINB / VGB_GENO8_MINB / VGB_GENO4_MINB: register budget variants (CTAs per SM the compiler must make room for)
+	int minb = 4, minb8 = 4, minb4 = 4;   // measured on B200 (profiles/r01_summary.md): 62 registers, no spills, 32 warps per SM beats 40 registers / 48 warps
 	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
 	if (const char *e = getenv("VGB_GENO8_MINB")) minb8 = atoi(e);
+	if (const char *e = getenv("VGB_GENO4_MINB")) minb4 = atoi(e);
 	const char *kk = getenv("VGB_GENO_KERNEL");
 	const bool warp_only = kk && !strcmp(kk, "warp");
+	g_use_quad = !(kk && !strcmp(kk, "oct"));
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
-	geno_kernel_t k8 = minb8 >= 8 ? k_geno8<8, false> : (minb8 >= 6 ? k_geno8<6, false> : (minb8 == 5 ? k_geno8<5, false> : (minb8 == 3 ? k_geno8<3, false> : k_geno8<4, false>)));
-	geno_kernel_t k8t = minb8 >= 8 ? k_geno8<8, true> : (minb8 >= 6 ? k_geno8<6, true> : (minb8 == 5 ? k_geno8<5, true> : (minb8 == 3 ? k_geno8<3, true> : k_geno8<4, true>)));
 	g_warp_kernel = k;
-	g_oct_kernel = warp_only ? nullptr : k8;
-	g_oct_kernel_trace = warp_only ? nullptr : k8t;
+	pick_group_kernels<4>(minb4, g_grp_kernel[0][0], g_grp_kernel[0][1]);
+	pick_group_kernels<8>(minb8, g_grp_kernel[1][0], g_grp_kernel[1][1]);
+	if (warp_only) g_grp_kernel[0][0] = g_grp_kernel[0][1] = g_grp_kernel[1][0] = g_grp_kernel[1][1] = nullptr;
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
 	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
-	const size_t smem8 = oct_smem_bytes();   // hit contexts + one row of counters per warp + the warp's parked reads
-	VGB_CUDA(c, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-	VGB_CUDA(c, cudaFuncSetAttribute(k8t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k8, GW * 32, smem8));
-	if (occ < 1) occ = 1;
-	g_oct_grid = (uint32_t)(c->sm_count * occ);
+	for (int gi = 0; gi < 2 && !warp_only; gi++) {
+		const size_t sm = grp_smem_bytes(gi ? 8 : 4);   // hit contexts + one row of counters per warp + the warp's parked reads
+		for (int t = 0; t < 2; t++) VGB_CUDA(c, cudaFuncSetAttribute(g_grp_kernel[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_grp_kernel[gi][0], GW * 32, sm));
+		if (occ < 1) occ = 1;
+		g_grp_grid[gi] = (uint32_t)(c->sm_count * occ);
+	}
 	if (!c->d_spill) {
 		Event *sp = nullptr;
 		int rc = dev_alloc(c, &sp, (uint64_t)c->geno_grid * GW * (EV_CAP - EV_SMEM));
@@ -544,10 +560,19 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.spill = (Event *)c->d_spill;
 	a.list = nullptr;
 	a.defer = ck.d_defer;
-	if (g_oct_kernel) {
-		// main kernel: 8 lanes per read; then the reads it deferred (long reads, context overflow) one warp per read
-		// per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernel carries none of it
-		(a.trace ? g_oct_kernel_trace : g_oct_kernel)<<<g_oct_grid, GW * 32, oct_smem_bytes(), c->stream>>>(a);
+	a.klist = nullptr;
+	a.kdefer = ck.d_defer2;
+	const int t = a.trace ? 1 : 0;   // per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernels carry none of it
+	if (g_grp_kernel[1][0]) {
+		// 4 lanes per read (up to 4 k-mers: 128..159 bases), then 8 lanes per read for what it handed over (5..8 k-mers), then
+		// one warp per read for the rest (longer reads, more hit contexts than the group kernels keep in shared memory)
+		if (g_use_quad) {
+			g_grp_kernel[0][t]<<<g_grp_grid[0], GW * 32, grp_smem_bytes(4), c->stream>>>(a);
+			a.klist = ck.d_defer2;
+			c->launches++;
+		}
+		a.kdefer = nullptr;
+		g_grp_kernel[1][t]<<<g_grp_grid[1], GW * 32, grp_smem_bytes(8), c->stream>>>(a);
 		a.list = ck.d_defer;
 		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches += 2;

@@ -1,36 +1,45 @@
-// vgb_geno8.inl -- the main per-read kernel: EIGHT lanes per read, four reads per warp, ONE PASS per round.
+// vgb_geno8.inl -- the main per-read kernel: G = 4 or 8 lanes per read, 32 / G reads per warp, ONE PASS per round.
 // Included by vgb_geno.cu.
 //
 // Same semantics as k_geno (one warp per read), different mapping.  A 150 bp read has 4 k-mers = 8 exact probes, so a
 // full warp per read leaves 24 lanes idle in the phases that matter and puts only one read's dependent probe chain in
-// flight per warp (profiles/r01_summary.md).  Here lane j of an octet owns k-mer j of its read for packing, exact probes,
-// Bloom gates and bucket bounds; neighbour tasks, the vote and the pileup contexts are spread over the octet's 8 lanes.
-// All four octets of a warp move through the phases together, so every warp-wide shuffle / ballot is executed
-// convergently; loops whose trip count differs per octet contain no warp-synchronous operation.
+// flight per warp (profiles/r01_summary.md).  Here lane j of a group owns k-mer j of its read for packing, exact probes,
+// Bloom gates and bucket bounds; neighbour tasks, the vote and the pileup contexts are spread over the group's lanes.
+// All groups of a warp move through the phases together, so every warp-wide shuffle / ballot is executed convergently;
+// loops whose trip count differs per group contain no warp-synchronous operation.
+//
+// Three kernels run per chunk: G = 4 over every read (up to 4 k-mers = up to 159 bases: eight reads and eight probe
+// chains per warp), G = 8 over the reads that one handed over (5..8 k-mers), then k_geno (one warp per read) over what is
+// left: longer reads and reads with more than OCT_EV hit contexts in a pass (a.defer / meta[6]; bit 31 of the list entry
+// = the forward pass is already done and accounted for here).
 //
 // Rounds: a warp round runs ONE pass (src/qv.cc:778-1510 is "forward pass, then one retry on the reverse complement",
-// :1504-1510) for four reads.  Reads whose forward pass places nothing are parked in a small per-warp queue (packed
-// k-mers + quality gates, 80 B) and the warp runs a retry round as soon as four are waiting -- so the second pass, which
-// half of all reads need (reverse-strand reads), is executed with four busy octets instead of one or two.
-//
-// Reads with more than 8 k-mers (>= 288 bases) or more than OCT_EV hit contexts in a pass are handed to k_geno in list
-// mode (a.defer / meta[6]); bit 31 of the list entry = the forward pass is already done and accounted for here.
+// :1504-1510) for 32 / G reads.  Reads whose forward pass places nothing are parked in a small per-warp queue (packed
+// k-mers + quality gates) and the warp runs a retry round as soon as a full set is waiting -- so the second pass, which
+// half of all reads need (reverse-strand reads), is executed with every group busy instead of half of them.
 
 constexpr int OCT_EV = 24;            // hit contexts per read kept in shared memory
-constexpr int PEND_CAP = 8;           // parked reads per warp: at most 3 waiting + 4 from one forward round
 
-// per-round counters of one read, in the octet's shared memory (committed when the round ends, unless the read is
+// per-round counters of one read, in the group's shared memory (committed when the round ends, unless the read is
 // deferred in this round); the first eight A_* slots of the per-warp accumulator have the same meaning
 enum { S_EXACT, S_NBRQ, S_SCAN, S_BF, S_LOWQ, S_EVENTS, S_INCR, S_BIG };
 
+// hit context, 16 bytes: kmer_context.position is X + 32 * (k-mer index), because every context of k-mer i is recorded
+// with offset 32 i (src/qv.cc:850-937, 985-1101)
+struct __align__(8) GEvent {
+	uint64_t kmer;
+	uint32_t X;       // read position this context votes for
+	uint32_t meta;    // bits 0-7 modified base (0xFF none) | 8-15 k-mer index | 16 list (0 ref, 1 snp) | 17 votes
+};
 struct OctSmem {
-	Event ev[OCT_EV];
+	GEvent ev[OCT_EV];
 	uint32_t st[8];
 	uint32_t ev_count;
 	uint32_t pad;
 };
+template <int G>
 struct Pend {
-	uint64_t kmer[8];                 // forward-strand packed k-mers
+	uint64_t kmer[G];                 // forward-strand packed k-mers
 	uint32_t r, K, lowq, pad;         // read index in the chunk, k-mer count, quality gates (bit i = k-mer i)
 };
 
@@ -38,8 +47,8 @@ __device__ __forceinline__ void emit8(OctSmem *os, uint64_t kmer, uint32_t pos, 
 {
 	const uint32_t i = atomicAdd(&os->ev_count, 1u);
 	if (i >= OCT_EV) return;                                  // overflow: the read is deferred after this pass
-	Event e;
-	e.kmer = kmer; e.X = pos - offset; e.kpos = pos; e.meta = mod | (kidx << 8) | (list << 16); e.pad = 0;
+	GEvent e;
+	e.kmer = kmer; e.X = pos - offset; e.meta = mod | (kidx << 8) | (list << 16);
 	os->ev[i] = e;
 }
 
@@ -115,22 +124,29 @@ __device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &nmask, uint3
 	return ((uint64_t)khi << 32) | klo;
 }
 
-template <int MINB, bool TRACE>
+template <int MINB, bool TRACE, int G>
 __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 {
+	static_assert(G == 4 || G == 8, "lanes per read");
+	constexpr uint32_t R = 32 / G;                // reads per warp round
+	constexpr uint32_t GM = (1u << G) - 1u;
+	constexpr int PEND_CAP = 2 * R;               // parked reads per warp: at most R - 1 waiting + R from one forward round
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t ol = lane & 7;                 // lane inside the octet = k-mer index this lane owns
-	const uint32_t ob = lane & 24;                // first lane of the octet
-	OctSmem *os = reinterpret_cast<OctSmem *>(smem_raw) + (threadIdx.x >> 3);
+	const uint32_t ol = lane & (G - 1);           // lane inside the group = k-mer index this lane owns
+	const uint32_t ob = lane & ~(uint32_t)(G - 1);   // first lane of the group
+	const uint32_t gi = lane / G;                 // group inside the warp
+	OctSmem *os = reinterpret_cast<OctSmem *>(smem_raw) + (threadIdx.x / G);
 	// one row of 16 counters per warp, then the warp's queue of parked reads
-	uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * 4) + (threadIdx.x >> 5) * 16;
-	Pend *pend = reinterpret_cast<Pend *>(smem_raw + sizeof(OctSmem) * GW * 4 + GW * 16 * sizeof(uint32_t)) + (threadIdx.x >> 5) * PEND_CAP;
+	uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * R) + (threadIdx.x >> 5) * 16;
+	Pend<G> *pend = reinterpret_cast<Pend<G> *>(smem_raw + sizeof(OctSmem) * GW * R + GW * 16 * sizeof(uint32_t)) + (threadIdx.x >> 5) * PEND_CAP;
 	const DevIndex &ix = a.ix;
-	const uint32_t n_reads = a.meta[1];
+	// list mode (the 8-lane instantiation behind the 4-lane one): only the reads the 4-lane kernel handed over (5..8 k-mers)
+	const uint32_t n_reads = a.klist ? a.meta[9] : a.meta[1];
+	uint32_t *work = a.meta + (a.klist ? 10 : 2);
 	const uint32_t FULL = 0xffffffffu;
 #define OSHFL(v, src) __shfl_sync(FULL, (v), ob | (src))
-#define OBALLOT(p) ((__ballot_sync(FULL, (p)) >> ob) & 0xFFu)
+#define OBALLOT(p) ((__ballot_sync(FULL, (p)) >> ob) & GM)
 	enum { A_EXACT, A_NBRQ, A_SCAN, A_BF, A_LOWQ, A_EVENTS, A_INCR, A_BIG, A_READS, A_SKIPPED, A_PASSES, A_PLACED, A_BAD, A_WRAP };
 	if (lane < 16) acc[lane] = 0;
 	__syncwarp();
@@ -140,16 +156,16 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 	for (;;) {
 		uint32_t pass, r = 0, K = 0;
-		bool have = false, run = false, defer = false, bad = false, skipped = false, lowq = false;
+		bool have = false, run = false, defer = false, wide = false, bad = false, skipped = false, lowq = false;
 		uint64_t kmer = 0;
 
-		if (npend >= 4 || (!fresh_left && npend)) {
-			// ---- retry round: up to four parked reads, on the reverse complement (src/qv.cc:787-806 on the packed form) ----
+		if (npend >= R || (!fresh_left && npend)) {
+			// ---- retry round: up to R parked reads, on the reverse complement (src/qv.cc:787-806 on the packed form) ----
 			pass = 1;
-			const uint32_t take = min(npend, 4u);
-			have = (lane >> 3) < take;
+			const uint32_t take = min(npend, R);
+			have = gi < take;
 			if (have) {
-				const Pend *p = &pend[npend - 1 - (lane >> 3)];
+				const Pend<G> *p = &pend[npend - 1 - gi];
 				r = p->r; K = p->K; lowq = (p->lowq >> ol) & 1u;
 				if (ol < K) kmer = revcomp64(p->kmer[K - 1 - ol]);
 				run = true;
@@ -158,22 +174,24 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		} else {
 			if (!fresh_left) break;
 			uint32_t r0 = 0;
-			if (lane == 0) r0 = atomicAdd(&a.meta[2], 4u);
+			if (lane == 0) r0 = atomicAdd(work, R);
 			r0 = __shfl_sync(FULL, r0, 0);
 			if (r0 >= n_reads) { fresh_left = false; continue; }
 			pass = 0;
-			r = r0 + (lane >> 3);
-			have = r < n_reads;
+			have = r0 + gi < n_reads;
+			if (have) r = a.klist ? __ldg(a.klist + r0 + gi) : r0 + gi;
 
-			// ---- record framing (src/qv.cc:760-779) ----
-			const uint32_t lsv = (have && ol < 5) ? __ldg(a.line_start + 4ull * r + ol) : 0;
-			const uint32_t id_s = OSHFL(lsv, 0), seq_s = OSHFL(lsv, 1), sep_s = OSHFL(lsv, 2), qual_s = OSHFL(lsv, 3), next_s = OSHFL(lsv, 4);
+			// ---- record framing (src/qv.cc:760-779): line starts 4r .. 4r+4 ----
+			uint32_t lsv = 0, lsn = 0;
+			if (have && ol < 4) lsv = __ldg(a.line_start + 4ull * r + ol);
+			if (have && ol == 0) lsn = __ldg(a.line_start + 4ull * r + 4);
+			const uint32_t id_s = OSHFL(lsv, 0), seq_s = OSHFL(lsv, 1), sep_s = OSHFL(lsv, 2), qual_s = OSHFL(lsv, 3), next_s = OSHFL(lsn, 0);
 			const uint32_t L = sep_s - 1 - seq_s;
 			const uint32_t qlen = next_s - 1 - qual_s;
 			K = L >> 5;
 			const bool bad_frame = have && ((seq_s - 1 - id_s > 1022) || (L > 1022) || (qual_s - 1 - sep_s > 1022) || (qlen > 1022) || (qlen < K));
-			defer = have && !bad_frame && K > 8;
-			bool active = have && !bad_frame && !defer;
+			wide = have && !bad_frame && K > (uint32_t)G;       // more k-mers than this instantiation has lanes
+			bool active = have && !bad_frame && !wide;
 
 			// ---- 2-bit packing: lane j packs k-mer j (src/util.c:89-111) ----
 			uint32_t nm = 0, xm = 0;
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			const uint32_t offm = OBALLOT((nm | xm) != 0);
 			bad = bad_frame;
 			if (__any_sync(FULL, offm != 0)) {
-				// shuffles are warp-wide: every octet executes them, whether or not it has an offending k-mer
+				// shuffles are warp-wide: every group executes them, whether or not it has an offending k-mer
 				const uint32_t j = offm ? (uint32_t)__ffs(offm) - 1 : 0u;
 				const uint32_t nmj = OSHFL(nm, j), xmj = OSHFL(xm, j);
 				if (offm && active) {
@@ -197,6 +215,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		}
 
 		os->st[ol] = 0;
+		if (G == 4) os->st[ol + 4] = 0;
 		if (ol == 0) os->ev_count = 0;
 		__syncwarp();
 
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			else if (rB + sB) atomicAdd(&os->st[S_SCAN], rB + sB);
 		}
 
-		// ---- Hamming-1 neighbours: the octet works through its low-quality k-mers one at a time ----
+		// ---- Hamming-1 neighbours: the group works through its low-quality k-mers one at a time ----
 		uint32_t lm = OBALLOT(gates);
 		const uint32_t rounds = __reduce_max_sync(FULL, (uint32_t)__popc(lm));
 		for (uint32_t it = 0; it < rounds; it++) {
@@ -260,7 +279,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			const uint32_t n3 = k_big ? 48u : k_rB;           // lower half, ref: queries (:975) or strided scan (:358-373)
 			const uint32_t n4 = k_big ? 48u : k_sB;           // lower half, snp: queries (:977) or strided scan (:447-462)
 			const uint32_t e0 = n0, e1 = e0 + n1, e2 = e1 + n2, e3 = e2 + n3, e4 = e3 + n4;
-			for (uint32_t t = ol; t < e4; t += 8) {
+			for (uint32_t t = ol; t < e4; t += G) {
 				// every kind of task ends in "a dictionary entry was found" -> one shared tail (hit8)
 				bool hit = false;
 				uint32_t list = 0, v = 0, fi = 0, d = 0;
@@ -309,18 +328,19 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		__syncwarp();
 
 		// ---- vote (src/qv.cc:132-178, order-independent form) ----
+		// two contexts with the same X come from different k-mer positions iff their k-mer indices differ (kmer_pos = X + 32 i)
 		uint32_t E = run ? os->ev_count : 0;
 		if (run && ol == 0) os->st[S_EVENTS] = E;
 		if (E > OCT_EV) { defer = true; E = 0; }              // too many contexts for shared memory: redo this pass in k_geno
 		const bool vrun = run && !defer;
-		for (uint32_t e = ol; e < E; e += 8) {
-			Event *p = &os->ev[e];
+		for (uint32_t e = ol; e < E; e += G) {
+			GEvent *p = &os->ev[e];
 			const uint32_t m = p->meta, X = p->X;
 			bool vt = (m & 0xFF) == NO_MOD;
 			if (!vt) {
 				const uint32_t ki = (m >> 8) & 0xFF;
 				for (uint32_t f = 0; f < E && !vt; f++) {
-					const Event *q = &os->ev[f];
+					const GEvent *q = &os->ev[f];
 					vt = ((q->meta & 0xFF) == NO_MOD) && q->X == X && ((q->meta >> 8) & 0xFF) <= ki;
 				}
 			}
@@ -330,31 +350,31 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		uint32_t bf_ = 0, bxmin = 0xFFFFFFFFu, bxmax = 0;
 		uint32_t t_nref = 0, t_nsnp = 0;
 		uint64_t t_dg = 0;
-		for (uint32_t e = ol; e < E; e += 8) {
-			const Event *p = &os->ev[e];
-			const uint32_t m = p->meta, X = p->X, kp = p->kpos;
+		for (uint32_t e = ol; e < E; e += G) {
+			const GEvent *p = &os->ev[e];
+			const uint32_t m = p->meta, X = p->X, ki = (m >> 8) & 0xFF;
 			if (TRACE) {
 				if ((m >> 16) & 1) t_nsnp++; else t_nref++;
-				t_dg += ctx_digest((m >> 16) & 1, X, kp, p->kmer, (m & 0xFF) == NO_MOD ? 10086u : (m & 0xFF));
+				t_dg += ctx_digest((m >> 16) & 1, X, X + 32u * ki, p->kmer, (m & 0xFF) == NO_MOD ? 10086u : (m & 0xFF));
 			}
 			if (!((m >> 17) & 1)) continue;
 			uint32_t f = 0;
 			bool distinct = false;
 			for (uint32_t g = 0; g < E; g++) {
-				const Event *q = &os->ev[g];
-				if (((q->meta >> 17) & 1) && q->X == X) { f++; distinct |= (q->kpos != kp); }
+				const GEvent *q = &os->ev[g];
+				if (((q->meta >> 17) & 1) && q->X == X) { f++; distinct |= (((q->meta >> 8) & 0xFF) != ki); }
 			}
 			if (!distinct) continue;
 			if (f > bf_) { bf_ = f; bxmin = X; bxmax = X; }
 			else if (f == bf_) { bxmin = min(bxmin, X); bxmax = max(bxmax, X); }
 		}
-		// octet reductions (xor 1, 2, 4 stay inside the octet)
+		// group reductions (xor offsets below G stay inside the group)
 		uint32_t maxf = bf_;
 #pragma unroll
-		for (int o = 1; o < 8; o <<= 1) maxf = max(maxf, __shfl_xor_sync(FULL, maxf, o));
+		for (int o = 1; o < G; o <<= 1) maxf = max(maxf, __shfl_xor_sync(FULL, maxf, o));
 		uint32_t xmin = bf_ == maxf ? bxmin : 0xFFFFFFFFu, xmax = bf_ == maxf ? bxmax : 0u;
 #pragma unroll
-		for (int o = 1; o < 8; o <<= 1) {
+		for (int o = 1; o < G; o <<= 1) {
 			xmin = min(xmin, __shfl_xor_sync(FULL, xmin, o));
 			xmax = max(xmax, __shfl_xor_sync(FULL, xmax, o));
 			if (TRACE) {
@@ -369,19 +389,21 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		const uint32_t target = xmin;
 		const bool retry = vrun && !process && pass == 0;       // park it: one retry on the reverse complement (:1504-1510)
 
-		// ---- park the reads that go to a retry round (warp-wide compaction over the octet leaders) ----
+		// ---- park the reads that go to a retry round (warp-wide compaction over the group leaders) ----
 		const uint32_t lowqm = OBALLOT(lowq);
 		const uint32_t rmask = __ballot_sync(FULL, retry && ol == 0);
 		if (retry) {
-			Pend *p = &pend[npend + __popc(rmask & ((1u << ob) - 1u))];
+			Pend<G> *p = &pend[npend + __popc(rmask & ((1u << ob) - 1u))];
 			p->kmer[ol] = kmer;
 			if (ol == 0) { p->r = r; p->K = K; p->lowq = lowqm; }
 		}
 		npend += __popc(rmask);
 
-		// ---- per-read bookkeeping (lane 0 of the octet speaks for the read) ----
+		// ---- per-read bookkeeping (lane 0 of the group speaks for the read) ----
 		if (have && ol == 0) {
-			if (defer) {
+			if (wide && G == 4) {
+				a.kdefer[atomicAdd(&a.meta[9], 1u)] = r;          // 5..8 k-mers: the 8-lane instantiation takes it, from the start
+			} else if (wide || defer) {
 				a.defer[atomicAdd(&a.meta[6], 1u)] = r | (pass << 31);
 			} else {
 				if (run) { atomicAdd(&acc[A_PASSES], 1u); os->st[S_EXACT] = 2u * K; os->st[S_BF] = 2u * os->st[S_LOWQ]; }
@@ -409,12 +431,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		// ---- pileup update: every recorded context at the winning position (src/qv.cc:1382-1502), one lane per context ----
 		if (process) {
 			const uint64_t n_blk = ix.pile_len >> 6;
-			for (uint32_t e = ol; e < E; e += 8) {
-				const Event *p = &os->ev[e];
+			for (uint32_t e = ol; e < E; e += G) {
+				const GEvent *p = &os->ev[e];
 				if (p->X != target) continue;
 				const uint32_t mod = p->meta & 0xFF;
 				const uint64_t kmer_e = p->kmer;
-				const uint64_t kpos = p->kpos;
+				const uint64_t kpos = (uint64_t)(uint32_t)(target + 32u * ((p->meta >> 8) & 0xFF));
 				// the 32-position window [kpos, kpos+32) lies in one or two 64-position blocks of the site bitmap
 				const uint64_t bA = kpos >> 6, bB = (kpos + 31) >> 6;
 				uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
@@ -441,10 +463,11 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			}
 		}
 		__syncwarp();
-		// commit the round's counters (lane ol commits counter ol: S_* and A_* share the first 8 slots)
-		if (have && !defer) {
+		// commit the round's counters (S_* and A_* share the first 8 slots)
+		if (have && !defer && !wide) {
 			const uint32_t cv = os->st[ol];
 			if (cv) atomicAdd(&acc[ol], cv);
+			if (G == 4) { const uint32_t cw = os->st[ol + 4]; if (cw) atomicAdd(&acc[ol + 4], cw); }
 		}
 		__syncwarp();
 	}

@@ -22,8 +22,9 @@ struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i
 	char *h_pinned = nullptr;         // pinned staging buffer handed out by vgb_pinned_buffer
 	uint32_t *d_line_start = nullptr; // [max_lines + 1] byte offset of each line start
 	uint32_t *d_blk_counts = nullptr; // newline count per 4 KiB tile, then its exclusive scan
-	uint32_t *d_defer = nullptr;      // read indices the 8-lane kernel hands to the warp-per-read kernel
-	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter
+	uint32_t *d_defer = nullptr;      // read indices the group kernels hand to the warp-per-read kernel
+	uint32_t *d_defer2 = nullptr;     // read indices the 4-lane kernel hands to the 8-lane kernel
+	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter
 	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, g0 = nullptr;
 	bool busy = false;
 };
