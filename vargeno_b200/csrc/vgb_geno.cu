@@ -470,7 +470,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 		}
 	}
 
-	// ---- statistics: one set of atomics per warp ----
+	// ---- statistics: one set of atomics per warp that did anything (an empty deferred list costs nothing) ----
+	if (w_reads == 0) return;
 	unsigned long long v[8] = { st.exact, st.nbrq, st.scan, st.bf, st.lowq, st.events, st.incr, st.big };
 #pragma unroll
 	for (int k = 0; k < 8; k++) {

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 #define OSHFL(v, src) __shfl_sync(FULL, (v), ob | (src))
 #define OBALLOT(p) ((__ballot_sync(FULL, (p)) >> ob) & GM)
 	enum { A_EXACT, A_NBRQ, A_SCAN, A_BF, A_LOWQ, A_EVENTS, A_INCR, A_BIG, A_READS, A_SKIPPED, A_PASSES, A_PLACED, A_BAD, A_WRAP };
+	if (n_reads == 0) return;                     // list mode with nothing handed over (the usual case for 150 bp reads)
 	if (lane < 16) acc[lane] = 0;
 	__syncwarp();
 
@@ -474,16 +475,24 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 #undef OSHFL
 #undef OBALLOT
 
-	__syncwarp();
-	if (lane == 0) {
+	// ---- statistics: one set of atomics per CTA, and only for counters that moved ----
+	__syncthreads();
+	if (threadIdx.x < 14) {
+		uint32_t *all = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * R);
+		unsigned long long v = 0;
+#pragma unroll
+		for (int w = 0; w < GW; w++) v += all[w * 16 + threadIdx.x];
 		DevStats *s = a.stats;
-		atomicAdd(&s->reads, (unsigned long long)acc[A_READS]); atomicAdd(&s->skipped_n, (unsigned long long)acc[A_SKIPPED]);
-		atomicAdd(&s->passes, (unsigned long long)acc[A_PASSES]); atomicAdd(&s->placed, (unsigned long long)acc[A_PLACED]);
-		atomicAdd(&s->exact_lookups, (unsigned long long)acc[A_EXACT]); atomicAdd(&s->nbr_query_lookups, (unsigned long long)acc[A_NBRQ]);
-		atomicAdd(&s->nbr_scan_reads, (unsigned long long)acc[A_SCAN]); atomicAdd(&s->bf_probes, (unsigned long long)acc[A_BF]);
-		atomicAdd(&s->lowq_kmers, (unsigned long long)acc[A_LOWQ]); atomicAdd(&s->events, (unsigned long long)acc[A_EVENTS]);
-		atomicAdd(&s->pileup_incr, (unsigned long long)acc[A_INCR]); atomicAdd(&s->big_kmers, (unsigned long long)acc[A_BIG]);
-		if (acc[A_BAD]) atomicAdd(&s->bad_records, (unsigned long long)acc[A_BAD]);
-		if (acc[A_WRAP]) atomicAdd(&s->freq_wrap_reads, (unsigned long long)acc[A_WRAP]);
+		unsigned long long *dst = nullptr;
+		switch (threadIdx.x) {
+		case A_EXACT: dst = &s->exact_lookups; break;   case A_NBRQ: dst = &s->nbr_query_lookups; break;
+		case A_SCAN: dst = &s->nbr_scan_reads; break;   case A_BF: dst = &s->bf_probes; break;
+		case A_LOWQ: dst = &s->lowq_kmers; break;       case A_EVENTS: dst = &s->events; break;
+		case A_INCR: dst = &s->pileup_incr; break;      case A_BIG: dst = &s->big_kmers; break;
+		case A_READS: dst = &s->reads; break;           case A_SKIPPED: dst = &s->skipped_n; break;
+		case A_PASSES: dst = &s->passes; break;         case A_PLACED: dst = &s->placed; break;
+		case A_BAD: dst = &s->bad_records; break;       default: dst = &s->freq_wrap_reads; break;
+		}
+		if (v) atomicAdd(dst, v);
 	}
 }
