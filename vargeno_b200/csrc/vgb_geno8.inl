@@ -18,7 +18,7 @@
 // k-mers + quality gates) and the warp runs a retry round as soon as a full set is waiting -- so the second pass, which
 // half of all reads need (reverse-strand reads), is executed with every group busy instead of half of them.
 
-constexpr int OCT_EV = 24;            // hit contexts per read kept in shared memory
+constexpr int OCT_EV = 24;            // hit contexts per read kept in shared memory (16 measured the same on S1 and at GRCh38 size)
 
 // per-round counters of one read, in the group's shared memory (committed when the round ends, unless the read is
 // deferred in this round); the first eight A_* slots of the per-warp accumulator have the same meaning
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						const int dd = one_base_slot((uint64_t)((uint32_t)km ^ entry_lo));
 						if (dd >= 0) { hit = true; nb = (km & 0xFFFFFFFF00000000ull) | entry_lo; v = ldr(&ix.ref[k_rlo + s].posx); d = (uint32_t)dd; }
 					}
-				} else {                                          // snp strided scan step (F13)
+				} else {                                          // snp strided scan step (F13).  Tried and not kept (profiles/r01_summary.md):
+				                                                  // four steps per task (+3 % / +9 % at GRCh38 size, -8 % on S1), prefetching the column (+4 % / -9 %)
 					const uint32_t s = t - e3;
 					const uint64_t ex = (uint64_t)k_slo + (uint64_t)SNP_STRIDE * s;
 					if (ex < ix.n_snp) {
