@@ -141,15 +141,24 @@ def run_ours(args):
     g = Genotyper(device=local, max_chunk_bytes=batch_bytes + 4096, world_size=world, rank=rank, nccl_unique_id=uid)
     # S1 index: genome text, SNP list, reference-format index records and the GPU re-layout, all produced through the device
     # (vgb_build_index_device is byte-identical to `vargeno index`: tests/test_gpu_index_build.py); replicated on every rank
-    want_cpu = rank == 0 and world == 1 and not args.skip_cpu
-    wl = dw.build_s1(g, scale=args.scale, keep_host=want_cpu)
+    want_cpu = rank == 0 and world == 1 and not args.skip_cpu and args.workload == "s1"
+    if args.workload == "s1":
+        wl = dw.build_s1(g, scale=args.scale, keep_host=want_cpu)
+        sub_rate, lowq_prob, shape = S1_SUB_RATE, S1_LOWQ_PROB, "1M-SNP list, 150bp reads @0.5% subst, lowq 0.25 on first 4 quality chars"
+    else:
+        # BASELINE.json configs[2] / [3]: GRCh38-shaped reference, 12 M SNPs; ~89 GiB of HBM per GPU.
+        # The CPU baseline leg is skipped here (the oracle would need the 37 GB index image on the host).
+        contigs = [(n, max(64, int(l * args.scale))) for n, l in dw.GRCH38]
+        wl = dw.build(g, contigs, max(100, int(12_000_000 * args.scale)), seed=38, name="S2 GRCh38-shaped x%g" % args.scale)
+        sub_rate, lowq_prob = (0.005, 0.25) if args.workload == "s2" else (0.02, 1.0)
+        shape = "12M-SNP list, 150bp reads @%g%% subst, lowq %g on first 4 quality chars" % (sub_rate * 100, lowq_prob)
     if world > 1:
         g.allreduce()                       # NCCL connection set-up happens on the first collective: keep it out of the timed legs
 
     # synthetic reads, generated on the device (byte-identical twin of tools/synth.simulate_reads)
     d_reads = g.dalloc(nb * batch_bytes)
     first = rank * nb * B
-    dw.synth_batch(g, wl, d_reads, nb * B, first, S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS, REC_ID_WIDTH)
+    dw.synth_batch(g, wl, d_reads, nb * B, first, sub_rate, lowq_prob, S1_LOWQ_CHARS, REC_ID_WIDTH)
     # host copy in pinned memory for the end-to-end leg
     pinned = torch.empty(nb * batch_bytes, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
@@ -241,13 +250,13 @@ def run_ours(args):
             except Exception:
                 rs = None
         cpu = None
-        if world == 1 and not args.skip_cpu:
+        if want_cpu:
             cpu = cpu_port_baseline(wl.host_index, host[:min(B, args.cpu_sample) * rec_bytes(L)])
         out = {
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl.name + ", 1M-SNP list, 150bp reads @0.5% subst, lowq 0.25 on first 4 quality chars",
+            "config": {"workload": wl.name + ", " + shape,
                        "reads_per_step_per_gpu": B, "read_len": L, "fastq_bytes_per_step_per_gpu": batch_bytes,
                        "index": "replicated per GPU", "reads": "sharded across GPUs",
                        "l2": "every step streams a distinct batch larger than L2 (no flush needed)",
@@ -257,7 +266,7 @@ def run_ours(args):
             "lookups_per_read": d_lookups / max(1, st1["reads"] - st0["reads"]),
             "placed_fraction": (st1["placed"] - st0["placed"]) / max(1, st1["reads"] - st0["reads"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC["bytes"] * B / NCU_TRAFFIC["reads_per_launch"] if args.scale == 1.0 else None,
+                         "traffic": NCU_TRAFFIC["bytes"] * B / NCU_TRAFFIC["reads_per_launch"] if (args.scale == 1.0 and args.workload == "s1") else None,
                          "traffic_source": NCU_TRAFFIC["source"],
                          "kernel": "k_geno8 (+ list-mode k_geno for deferred reads)", "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": d_ms_geno / K,
                          "peak_source": peak_src, "note": "32 B (one DRAM sector) per dictionary lookup, SURVEY.md 8(d)",
@@ -424,7 +433,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the S1 genome / SNP list (tests only)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome / SNP list (tests only)")
+    ap.add_argument("--workload", default="s1", choices=["s1", "s2", "s3"],
+                    help="s1: chr22-shaped (BASELINE configs[1], the default); s2 / s3: GRCh38-shaped WGS / high-error stress (configs[2] / [3])")
     ap.add_argument("--batch-reads", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--ref-batch-reads", type=int, default=100_000)

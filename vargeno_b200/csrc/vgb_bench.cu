@@ -37,7 +37,7 @@ int lookup_kmers(vgb_ctx *c, const uint64_t *kmers, uint64_t n, vgb_hit *out)
 {
 	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
 	if (n == 0) return VGB_OK;
-	uint64_t *d_k; vgb_hit *d_h;
+	uint64_t *d_k = nullptr; vgb_hit *d_h = nullptr;
 	int rc;
 	if ((rc = dev_alloc(c, &d_k, n, false))) return rc;
 	if ((rc = dev_alloc(c, &d_h, n, false))) { cudaFree(d_k); return rc; }
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_probe(const DevIndex ix, const uint64_t
 int probe_bench(vgb_ctx *c, uint64_t n, int mode, uint64_t seed, int repeats, double *ms, uint64_t *found)
 {
 	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
-	uint64_t *d_k; unsigned long long *d_f;
+	uint64_t *d_k = nullptr; unsigned long long *d_f = nullptr;
 	int rc;
 	if ((rc = dev_alloc(c, &d_k, n, false))) return rc;
 	if ((rc = dev_alloc(c, &d_f, 1, false))) { cudaFree(d_k); return rc; }
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_random_sectors(const uint4 *buf, uint64
 
 int random_sector_bench(vgb_ctx *c, uint64_t bytes, uint64_t n_loads, int repeats, double *gbs)
 {
-	uint4 *d_buf; unsigned long long *d_sink;
+	uint4 *d_buf = nullptr; unsigned long long *d_sink = nullptr;
 	int rc;
 	if ((rc = dev_alloc(c, &d_buf, bytes / 16, false))) return rc;
 	if ((rc = dev_alloc(c, &d_sink, 1, false))) { cudaFree(d_buf); return rc; }
@@ -230,7 +230,7 @@ int synth_reads(vgb_ctx *c, const uint8_t *hap0, const uint8_t *hap1, uint64_t g
 	const uint64_t rec = 2 + id_width + 1 + read_len + 3 + read_len + 1;
 	if (n_reads * rec > out_cap) return set_err(c, VGB_E_ARG, "output buffer too small: need %llu bytes", (unsigned long long)(n_reads * rec));
 	if (id_width > 19 || read_len == 0 || genome_len < read_len) return set_err(c, VGB_E_ARG, "bad synth parameters");
-	uint64_t *d_cs, *d_cl;
+	uint64_t *d_cs = nullptr, *d_cl = nullptr;
 	int rc;
 	if ((rc = dev_alloc(c, &d_cs, n_contigs, false))) return rc;
 	if ((rc = dev_alloc(c, &d_cl, n_contigs, false))) { cudaFree(d_cs); return rc; }

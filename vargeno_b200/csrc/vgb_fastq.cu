@@ -119,14 +119,16 @@ __global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_
 }
 
 template <int T, int PER>
-static void launch_fq_index(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t line_cap, cudaStream_t st)
+static cudaError_t launch_fq_index(Chunk &ck, uint64_t nbytes, uint64_t line_cap, cudaStream_t st)
 {
 	const uint64_t n_tiles = (nbytes + (uint64_t)T * PER - 1) / ((uint64_t)T * PER);
 	unsigned long long *status = reinterpret_cast<unsigned long long *>(ck.d_blk_counts);   // >= max_chunk_bytes / 512 bytes
-	cudaMemsetAsync(status, 0, n_tiles * sizeof(unsigned long long), st);
-	cudaMemsetAsync(ck.d_meta + 8, 0, sizeof(uint32_t), st);                               // tile counter
+	cudaError_t e = cudaMemsetAsync(status, 0, n_tiles * sizeof(unsigned long long), st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(ck.d_meta + 8, 0, sizeof(uint32_t), st);    // tile counter
+	if (e != cudaSuccess) return e;
 	k_fq_index<T, PER><<<(unsigned)n_tiles, T, 0, st>>>(ck.d_text, nbytes, (uint32_t)n_tiles, status, ck.d_meta + 8, ck.d_meta + 4,
 	                                                   ck.d_line_start, line_cap);
+	return cudaSuccess;
 }
 
 int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
@@ -135,11 +137,13 @@ int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
 	const int variant = getenv("VGB_FQ_VARIANT") ? atoi(getenv("VGB_FQ_VARIANT")) : 0;   // tuning aid (tools/perf_sweep.py)
 	// measured on B200, 632 MB of FASTQ (profiles/r01_summary.md): 256 x 256 B 0.225 ms, 128 x 256 B 0.235, 512 x 128 B 0.262,
 	// 256 x 128 B 0.267, 128 x 128 B 0.281, 1024 x 64 B 0.293 -- bytes in flight per thread matter more than the tile size
+	cudaError_t e;
 	switch (variant) {
-	case 1: launch_fq_index<512, 128>(c, ck, nbytes, line_cap, st); break;
-	case 2: launch_fq_index<256, 512>(c, ck, nbytes, line_cap, st); break;
-	default: launch_fq_index<256, 256>(c, ck, nbytes, line_cap, st); break;
+	case 1: e = launch_fq_index<512, 128>(ck, nbytes, line_cap, st); break;
+	case 2: e = launch_fq_index<256, 512>(ck, nbytes, line_cap, st); break;
+	default: e = launch_fq_index<256, 256>(ck, nbytes, line_cap, st); break;
 	}
+	VGB_CUDA(c, e);
 	k_fq_finish<<<1, 1, 0, st>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap);
 	c->launches += 2;
 	VGB_CUDA(c, cudaGetLastError());

@@ -395,13 +395,13 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	DevIndex &ix = c->ix;
 	int rc;
 
-	ParseOut *d_po; uint32_t *d_tmp;
+	ParseOut *d_po = nullptr; uint32_t *d_tmp = nullptr;
 	if ((rc = dev_alloc(c, &d_po, 1, false))) return rc;
 	if ((rc = dev_alloc(c, &d_tmp, (1ull << 32) / SCAN_TILE + 8, false))) return rc;
 	VGB_CUDA(c, cudaMemsetAsync(d_po, 0, sizeof(ParseOut), c->stream));
 
 	// ---- reference dictionary ----
-	RefEntry *d_ref, *d_by_lo; uint32_t *d_jg, *d_jg_lo; uint32_t *d_aux;
+	RefEntry *d_ref = nullptr, *d_by_lo = nullptr; uint32_t *d_jg = nullptr, *d_jg_lo = nullptr; uint32_t *d_aux = nullptr;
 	if ((rc = dev_alloc(c, &d_ref, v->n_ref))) return rc;
 	if ((rc = dev_alloc(c, &d_by_lo, v->n_ref))) return rc;
 	if ((rc = dev_alloc(c, &d_jg, (1ull << 32) + 1))) return rc;
@@ -432,7 +432,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	// ---- SNP dictionary + static pileup ----
 	// SNP k-mer starts are reference k-mer starts, so sites lie below max_pos + 32 (src/qv.cc:596-603)
 	const uint64_t pile_len = (((uint64_t)po.max_pos + 32 + 1) + 63) / 64 * 64;
-	SnpEntry *d_snp; uint32_t *d_sjg, *d_sjg30, *d_sap, *d_lw; uint8_t *d_sai;
+	SnpEntry *d_snp = nullptr; uint32_t *d_sjg, *d_sjg30, *d_sap, *d_lw; uint8_t *d_sai;
 	if ((rc = dev_alloc(c, &d_snp, v->n_snp))) return rc;
 	if ((rc = dev_alloc(c, &d_sjg, (1ull << 24) + 1))) return rc;
 	if ((rc = dev_alloc(c, &d_sjg30, (1ull << 30) + 1))) return rc;
@@ -461,7 +461,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	{
 		// residue-major LO40 column for the strided scan
 		const uint64_t stride = (v->n_snp + SNP_STRIDE - 1) / SNP_STRIDE + 1;
-		uint64_t *d_scan;
+		uint64_t *d_scan = nullptr;
 		if ((rc = dev_alloc(c, &d_scan, stride * SNP_STRIDE))) return rc;
 		VGB_CUDA(c, cudaMemsetAsync(d_scan, 0, stride * SNP_STRIDE * 8, c->stream));
 		if (v->n_snp) k_snp_scan_layout<<<(unsigned)((v->n_snp + 255) / 256), 256, 0, c->stream>>>(d_snp, v->n_snp, stride, d_scan);
@@ -474,7 +474,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 
 	// site bitmap + rank directory + compact per-site arrays
 	const uint64_t n_blk = pile_len / 64;
-	uint32_t *d_bits32, *d_popc, *d_rank, *d_total; PileBlk *d_pile;
+	uint32_t *d_bits32 = nullptr, *d_popc = nullptr, *d_rank = nullptr, *d_total = nullptr; PileBlk *d_pile = nullptr;
 	if ((rc = dev_alloc(c, &d_bits32, pile_len / 32, false))) return rc;
 	if ((rc = dev_alloc(c, &d_popc, n_blk, false))) return rc;
 	if ((rc = dev_alloc(c, &d_rank, n_blk, false))) return rc;
@@ -489,7 +489,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	uint32_t n_sites = 0;
 	VGB_CUDA(c, cudaMemcpyAsync(&n_sites, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
-	uint8_t *d_code; uint32_t *d_cnt;
+	uint8_t *d_code = nullptr; uint32_t *d_cnt;
 	if ((rc = dev_alloc(c, &c->d_site_pos, n_sites))) return rc;
 	if ((rc = dev_alloc(c, &d_code, n_sites))) return rc;
 	if ((rc = dev_alloc(c, &c->d_site_rf, n_sites))) return rc;
