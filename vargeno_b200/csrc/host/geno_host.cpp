@@ -164,7 +164,35 @@ struct FastqSource {
 };
 }  // namespace
 
+namespace {
+// the real sink: contexts round robin, two pinned slots each
+struct GpuSink : ChunkSink {
+	const std::vector<vgb_ctx *> &ctxs;
+	explicit GpuSink(const std::vector<vgb_ctx *> &c) : ctxs(c) {}
+	int buffer(size_t turn, char **buf, uint64_t *cap, std::string &err) override
+	{
+		vgb_ctx *ctx = ctxs[turn % ctxs.size()];
+		const int rc = vgb_pinned_buffer(ctx, (int)((turn / ctxs.size()) & 1), buf, cap);
+		if (rc != VGB_OK) err = vgb_last_error(ctx);
+		return rc;
+	}
+	int submit(size_t turn, const char *buf, uint64_t nbytes, uint64_t first_read, std::string &err) override
+	{
+		vgb_ctx *ctx = ctxs[turn % ctxs.size()];
+		const int rc = vgb_submit_fastq(ctx, buf, nbytes, first_read);
+		if (rc != VGB_OK) err = vgb_last_error(ctx);
+		return rc;
+	}
+};
+}  // namespace
+
 int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
+{
+	GpuSink sink(ctxs);
+	return stream_fastq_to(sink, path, chunk_bytes, n_chunks, err);
+}
+
+int stream_fastq_to(ChunkSink &sink, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
 {
 	FastqSource src;
 	{
@@ -181,12 +209,10 @@ int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, ui
 	bool eof = false;
 	int rc = VGB_OK;
 	while (!eof || !carry.empty()) {
-		vgb_ctx *ctx = ctxs[turn % ctxs.size()];
-		const int slot = (int)((turn / ctxs.size()) & 1);
-		turn++;
+		const size_t this_turn = turn++;
 		char *buf = nullptr;
 		uint64_t cap = 0;
-		if ((rc = vgb_pinned_buffer(ctx, slot, &buf, &cap)) != VGB_OK) { err = vgb_last_error(ctx); break; }
+		if ((rc = sink.buffer(this_turn, &buf, &cap, err)) != VGB_OK) break;
 		if (cap > chunk_bytes) cap = chunk_bytes;
 		uint64_t have = carry.size();
 		if (have > cap) { err = "a single FASTQ record is larger than the chunk size"; rc = VGB_E_FORMAT; break; }
@@ -215,11 +241,37 @@ int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, ui
 		} else if (have > 0 && buf[have - 1] != '\n') {
 			lines += 1;                                         // last line without newline
 		}
-		if ((rc = vgb_submit_fastq(ctx, buf, use, read_id)) != VGB_OK) { err = vgb_last_error(ctx); break; }
+		if ((rc = sink.submit(this_turn, buf, use, read_id, err)) != VGB_OK) break;
 		read_id += lines / 4;
 		n_chunks++;
 	}
 	return rc;
+}
+
+// `vargeno-b200 fastq-chunks`: the chunker alone, no GPU -- one line per chunk (bytes, lines, first read, FNV-1a of the bytes)
+int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes)
+{
+	struct PrintSink : ChunkSink {
+		std::vector<char> mem;
+		uint64_t total = 0, n = 0;
+		explicit PrintSink(uint64_t cap) : mem(cap) {}
+		int buffer(size_t, char **buf, uint64_t *cap, std::string &) override { *buf = mem.data(); *cap = mem.size(); return VGB_OK; }
+		int submit(size_t, const char *buf, uint64_t nbytes, uint64_t first_read, std::string &) override
+		{
+			uint64_t h = 1469598103934665603ull;
+			for (uint64_t i = 0; i < nbytes; i++) { h ^= (unsigned char)buf[i]; h *= 1099511628211ull; }
+			printf("%llu %llu %llu %llu %016llx\n", (unsigned long long)n++, (unsigned long long)nbytes, (unsigned long long)count_newlines(buf, nbytes),
+			       (unsigned long long)first_read, (unsigned long long)h);
+			total += nbytes;
+			return VGB_OK;
+		}
+	} sink(chunk_bytes);
+	uint64_t n_chunks = 0;
+	std::string err;
+	const int rc = stream_fastq_to(sink, fastq, chunk_bytes, n_chunks, err);
+	if (rc != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	printf("total %llu bytes in %llu chunks\n", (unsigned long long)sink.total, (unsigned long long)n_chunks);
+	return EXIT_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

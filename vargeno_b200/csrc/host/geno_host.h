@@ -37,9 +37,18 @@ struct IndexFiles {
 
 struct Call { char gt; double conf; };   // gt: '0' ref, '1' het, '2' alt (src/qv.cc:1606-1619)
 
-// Streams a FASTQ file through one or more contexts (round robin), record-aligned chunks in the contexts' pinned buffers.
-// Returns 0 or a VGB_E_* code (err filled).
+// Streams FASTQ input (one file or a comma-separated list read back to back; plain or gzip) through one or more contexts
+// (round robin), record-aligned chunks in the contexts' pinned buffers.  Returns 0 or a VGB_E_* code (err filled).
 int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err);
+
+// the chunker behind it, against any consumer of record-aligned chunks (the GPU contexts; a printer for the host-logic tests)
+struct ChunkSink {
+	virtual int buffer(size_t turn, char **buf, uint64_t *cap, std::string &err) = 0;       // where chunk number `turn` is assembled
+	virtual int submit(size_t turn, const char *buf, uint64_t nbytes, uint64_t first_read, std::string &err) = 0;
+	virtual ~ChunkSink() {}
+};
+int stream_fastq_to(ChunkSink &sink, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err);
+int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes);   // `vargeno-b200 fastq-chunks <files> [--chunk-bytes B]`
 
 // stage F on the host side: device calls -> "chr$pos" -> (gt, conf) map (src/qv.cc:1596-1621)
 int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::string, Call> &out, std::string &err);

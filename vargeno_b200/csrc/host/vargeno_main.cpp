@@ -53,6 +53,17 @@ int main(int argc, const char *argv[])
 		if (npos != 3 || dev < 0) { print_help(); return EXIT_FAILURE; }   // arg_check, src/qv.cc:1875-1881
 		return vgh::run_index(pos[0], pos[1], pos[2], dev, verbose, dump);
 	}
+	if (opt == "fastq-chunks") {      // host-logic check, no GPU: how the FASTQ input would be cut into record-aligned chunks
+		std::string files;
+		uint64_t bytes = 256ull << 20;
+		for (int i = 2; i < argc; i++) {
+			if (!strcmp(argv[i], "--chunk-bytes") && i + 1 < argc) bytes = strtoull(argv[++i], nullptr, 10);
+			else if (!strcmp(argv[i], "--chunk-mb") && i + 1 < argc) bytes = strtoull(argv[++i], nullptr, 10) << 20;
+			else files = argv[i];
+		}
+		if (files.empty() || bytes < 16) { print_help(); return EXIT_FAILURE; }
+		return vgh::run_fastq_chunks(files, bytes);
+	}
 	if (opt == "help") { print_help(); return EXIT_SUCCESS; }
 	print_help();
 	return EXIT_FAILURE;
