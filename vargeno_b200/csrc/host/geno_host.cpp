@@ -289,6 +289,12 @@ int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::stri
 		err = vgb_last_error(ctx);
 		return rc;
 	}
+	calls_to_map(pos.data(), gt.data(), conf.data(), n, chr, out);
+	return VGB_OK;
+}
+
+void calls_to_map(const uint32_t *pos, const uint8_t *gt, const double *conf, uint64_t n, const ChrLens &chr, std::unordered_map<std::string, Call> &out)
+{
 	for (uint64_t i = 0; i < n; i++) {                          // position order, like the scan of src/qv.cc:1573-1626
 		if (gt[i] == 0) continue;                               // GTYPE_NONE
 		std::string name;
@@ -297,7 +303,30 @@ int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::stri
 		const char g = gt[i] == 1 ? '0' : (gt[i] == 2 ? '2' : '1');   // REF '0', ALT '2', HET '1' (src/qv.cc:1606-1618)
 		out[name + "$" + std::to_string(rel)] = Call{ g, conf[i] };
 	}
-	return VGB_OK;
+}
+
+// `vargeno-b200 vcf-rewrite <prefix> <calls.tsv> <in.vcf> <out.vcf>`: stages F (host part) + G alone, no GPU.
+// calls.tsv: one line per site in position order: <1-based position in the concatenation> <gtype 0..3> <confidence (strtod)>
+int run_vcf_rewrite(const std::string &prefix, const std::string &calls_tsv, const std::string &vcf_in, const std::string &vcf_out)
+{
+	std::string err;
+	ChrLens chr;
+	if (!chr.load(prefix + ".chrlens", err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	std::ifstream in(calls_tsv);
+	if (!in.good()) { fprintf(stderr, "vargeno-b200: cannot open %s\n", calls_tsv.c_str()); return EXIT_FAILURE; }
+	std::vector<uint32_t> pos;
+	std::vector<uint8_t> gt;
+	std::vector<double> conf;
+	std::string a, b, c;
+	while (in >> a >> b >> c) {
+		pos.push_back((uint32_t)strtoull(a.c_str(), nullptr, 10));
+		gt.push_back((uint8_t)atoi(b.c_str()));
+		conf.push_back(strtod(c.c_str(), nullptr));
+	}
+	std::unordered_map<std::string, Call> calls;
+	calls_to_map(pos.data(), gt.data(), conf.data(), pos.size(), chr, calls);
+	if (rewrite_vcf(vcf_in, vcf_out, calls, err) != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	return EXIT_SUCCESS;
 }
 
 static std::vector<std::string> split(const std::string &text, char sep)

@@ -53,6 +53,9 @@ int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes);   // `varg
 // stage F on the host side: device calls -> "chr$pos" -> (gt, conf) map (src/qv.cc:1596-1621)
 int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::string, Call> &out, std::string &err);
 
+void calls_to_map(const uint32_t *pos, const uint8_t *gt, const double *conf, uint64_t n, const ChrLens &chr, std::unordered_map<std::string, Call> &out);
+int run_vcf_rewrite(const std::string &prefix, const std::string &calls_tsv, const std::string &vcf_in, const std::string &vcf_out);   // host-logic tests
+
 // stage G: VCF rewrite (src/qv.cc:1628-1747)
 int rewrite_vcf(const std::string &vcf_in, const std::string &vcf_out, const std::unordered_map<std::string, Call> &calls, std::string &err);
 

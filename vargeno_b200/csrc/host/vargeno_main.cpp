@@ -64,6 +64,10 @@ int main(int argc, const char *argv[])
 		if (files.empty() || bytes < 16) { print_help(); return EXIT_FAILURE; }
 		return vgh::run_fastq_chunks(files, bytes);
 	}
+	if (opt == "vcf-rewrite") {       // host-logic check, no GPU: chrlens mapping + GQ + VCF rewrite from a table of calls
+		if (argc != 6) { print_help(); return EXIT_FAILURE; }
+		return vgh::run_vcf_rewrite(argv[2], argv[3], argv[4], argv[5]);
+	}
 	if (opt == "help") { print_help(); return EXIT_SUCCESS; }
 	print_help();
 	return EXIT_FAILURE;
