@@ -81,12 +81,15 @@ __device__ __forceinline__ void hit8(const DevIndex &ix, OctSmem *os, uint32_t l
 	}
 }
 
-// 32 characters starting at p -> packed 32-mer (encode_kmer, src/util.c:89-111); nmask / xmask: bit b set if base b is
-// N/n / outside ACGTNacgtn.  Word-at-a-time: nine aligned 32-bit loads, funnel shifts, then per 4 characters
+// 32 characters starting at p -> packed 32-mer (encode_kmer, src/util.c:89-111).  `off`: 0 = all of ACGTacgt; otherwise
+// what encode_kmer meets first (it walks from the HIGHEST base down): 1 = an N/n (the read is skipped), 2 = a character
+// outside ACGTNacgtn (the reference aborts there; counted as a bad record here).
+// Word-at-a-time: nine aligned 32-bit loads, funnel shifts, then per 4 characters
 //   t = (c >> 1) & 3  ->  A 0, C 1, T 2, G 3;   code = t ^ (t >> 1)  ->  A 0, C 1, G 2, T 3
 // and the test "the case-folded character is the letter its code stands for" ('A' + {0, 2, 6, 19}) in one compare per
-// word.  Only a k-mer that fails it (N or a foreign character, rare) takes the byte-compare path for the two masks.
-__device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &nmask, uint32_t &xmask)
+// word; the last word that fails it holds the highest offending character.  (Recomputing per-base N / foreign masks with
+// byte compares for offending k-mers cost ~480 instructions per warp round on S1, where a fifth of the reads are N runs.)
+__device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &off)
 {
 	const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
 	const uint32_t sh = (uint32_t)(addr & 3) * 8;
@@ -94,7 +97,7 @@ __device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &nmask, uint3
 	uint32_t w[9];
 #pragma unroll
 	for (int i = 0; i < 9; i++) w[i] = __ldg(wp + i);
-	uint32_t klo = 0, khi = 0, badw = 0;
+	uint32_t klo = 0, khi = 0, bw = 0, uw = 0;
 #pragma unroll
 	for (int i = 0; i < 8; i++) {
 		const uint32_t u = __funnelshift_r(w[i], w[i + 1], sh) & 0xDFDFDFDFu;   // characters 4i .. 4i+3, case folded
@@ -102,24 +105,17 @@ __device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &nmask, uint3
 		const uint32_t code = t ^ ((t >> 1) & 0x01010101u);
 		const uint32_t b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u;
 		const uint32_t expect = 0x41414141u + 2u * b0 + 6u * b1 + 11u * (b0 & b1);
-		badw |= u ^ expect;
+		const uint32_t b = u ^ expect;
+		if (b) { bw = b; uw = u; }                                 // words ascend: the last one kept is the highest
 		// bytes {c0, c1, c2, c3} (2 bits each) -> one byte c0 | c1 << 2 | c2 << 4 | c3 << 6: the four partial products land
 		// on disjoint bit ranges, bits 24..31 of the 32-bit product are the packed byte
 		const uint32_t pk = (code * 0x01041040u) >> 24;
 		if (i < 4) klo |= pk << (8 * i); else khi |= pk << (8 * (i - 4));
 	}
-	nmask = 0; xmask = 0;
-	if (badw) {
-#pragma unroll 1
-		for (int i = 0; i < 8; i++) {
-			const uint32_t u = __funnelshift_r(__ldg(wp + i), __ldg(wp + i + 1), sh) & 0xDFDFDFDFu;
-			const uint32_t va = __vcmpeq4(u, 0x41414141u), vc = __vcmpeq4(u, 0x43434343u), vg = __vcmpeq4(u, 0x47474747u),
-			               vt = __vcmpeq4(u, 0x54545454u), vn = __vcmpeq4(u, 0x4E4E4E4Eu);
-			const uint32_t nb = vn & 0x01010101u;
-			const uint32_t xb = ~(va | vc | vg | vt | vn) & 0x01010101u;
-			nmask |= ((nb | (nb >> 7) | (nb >> 14) | (nb >> 21)) & 0xFu) << (4 * i);
-			xmask |= ((xb | (xb >> 7) | (xb >> 14) | (xb >> 21)) & 0xFu) << (4 * i);
-		}
+	off = 0;
+	if (bw) {
+		const uint32_t top = (31u - (uint32_t)__clz(bw)) & ~7u;   // bit offset of the highest offending character in its word
+		off = ((uw >> top) & 0xFFu) == 0x4Eu ? 1u : 2u;           // 'N' after case folding
 	}
 	return ((uint64_t)khi << 32) | klo;
 }
@@ -195,19 +191,15 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			bool active = have && !bad_frame && !wide;
 
 			// ---- 2-bit packing: lane j packs k-mer j (src/util.c:89-111) ----
-			uint32_t nm = 0, xm = 0;
-			if (active && ol < K) kmer = pack32(a.text + seq_s + 32u * ol, nm, xm);
+			uint32_t off = 0;
+			if (active && ol < K) kmer = pack32(a.text + seq_s + 32u * ol, off);
 			// the first k-mer with an N or a foreign character decides; inside it encode_kmer meets the HIGHEST base first
-			const uint32_t offm = OBALLOT((nm | xm) != 0);
+			const uint32_t offm = OBALLOT(off != 0);
 			bad = bad_frame;
 			if (__any_sync(FULL, offm != 0)) {
 				// shuffles are warp-wide: every group executes them, whether or not it has an offending k-mer
-				const uint32_t j = offm ? (uint32_t)__ffs(offm) - 1 : 0u;
-				const uint32_t nmj = OSHFL(nm, j), xmj = OSHFL(xm, j);
-				if (offm && active) {
-					const uint32_t top = 31 - __clz(nmj | xmj);
-					if ((xmj >> top) & 1u) bad = true; else skipped = true;
-				}
+				const uint32_t offj = OSHFL(off, offm ? (uint32_t)__ffs(offm) - 1 : 0u);
+				if (offm && active) { if (offj == 2u) bad = true; else skipped = true; }
 			}
 			if (bad || skipped) active = false;
 			// quality gate of k-mer i = i-th quality CHARACTER, signed compare (src/qv.cc:836,943; F8)
