@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_make_probe_kmers(const DevIndex ix, uin
 	// sampled dictionary entry: its HI32 is the jumpgate slot h with jg[h] <= idx < jg[h+1]
 	const uint32_t idx = (uint32_t)(r % ix.n_ref);
 	uint64_t lo = 0, hi = 1ull << 32;                     // invariant: jg[lo] <= idx, jg[hi] > idx
-	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (ix.ref_jg[mid] <= idx) lo = mid; else hi = mid; }
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (ref_jg_at(ix, mid) <= idx) lo = mid; else hi = mid; }
 	kmers[i] = (lo << 32) | ix.ref[idx].lo;
 }
 

@@ -41,7 +41,15 @@ struct __align__(16) PileBlk {
 
 struct DevIndex {
 	const RefEntry *ref;        uint64_t n_ref;
-	const uint32_t *ref_jg;     // 2^32 + 1 entries: ref_jg[h] = #entries with HI32 < h (src/qv.cc:539-584)
+	// Combined directory, one 20-byte record (5 words) per value p of the top 30 bits of a k-mer, 2^30 + 1 records:
+	//   words 0..3  ref_jg[4p .. 4p+3]   ref_jg[h] = #reference entries with HI32 < h (the reference's jumpgate, src/qv.cc:539-584)
+	//   word  4     snp_jg30[p]          #SNP entries whose top 30 bits are < p: exact SNP queries land in a block of ~0-2 entries
+	//                                    (a GRCh38-sized SNP dictionary has ~23 entries per HI24 block = 4-5 dependent sectors per query)
+	// The end of a block is the next start (word k+1, or word 0 / word 4 of the next record).  Same 20 GiB as two separate
+	// arrays, but both directory pairs of a k-mer's exact queries sit within 40 consecutive bytes: one L2 request (128-byte
+	// line) instead of two in 2 of 3 cases.  k_geno8 runs at the L2 request rate of this part (profiles/r01_summary.md), so
+	// requests per read are what its time is made of.
+	const uint32_t *xdir;
 	const uint32_t *ref_aux;    uint32_t n_ref_aux; uint32_t amb_lo;
 	// secondary view of the reference dictionary keyed by LO32: all entries that share the lower 16 bases sit in one
 	// bucket, so the 48 upper-half Hamming-1 neighbours of a k-mer (src/qv.cc:1213-1298) are answered by one bucket read
@@ -49,8 +57,6 @@ struct DevIndex {
 	const uint32_t *ref_jg_lo;  // 2^32 entries: END of the bucket of LO32 == l (start = end of bucket l-1, 0 for l == 0)
 	const SnpEntry *snp;        uint64_t n_snp;
 	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678): the HI24 block the strided scan needs
-	const uint32_t *snp_jg30;   // 2^30 + 1 entries, same idea on the top 30 bits: exact queries land in a block of ~0-2 entries
-	                            // (a GRCh38-sized SNP dictionary has ~23 entries per HI24 block = 4-5 dependent sectors per query)
 	// residue-major copy of the LO40 column for the strided scan (F13): step t of a scan that starts at rank lo examines rank
 	// lo + 11 t, i.e. one residue class mod 11 at consecutive quotients -- stored contiguously here, so the ~23 steps of a
 	// GRCh38-sized block touch ~6 sectors instead of 23:  snp_scan[(r % 11) * snp_scan_stride + r / 11] = LO40(entry r)
@@ -121,12 +127,16 @@ __device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
 	return (ldr(ix.snp_bf + w) >> (bit & 31)) & 1u;
 }
 
+// ref_jg[h] for h in [0, 2^32]
+__device__ __forceinline__ uint32_t ref_jg_at(const DevIndex &ix, uint64_t h) { return ldr(ix.xdir + (h >> 2) * 5 + (h & 3)); }
 // jumpgate pair of the HI32 block (src/qv.cc:219-233, check_block_size :242-264)
 __device__ __forceinline__ void ref_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
 	const uint64_t h = kmer >> 32;
-	lo = ldr(ix.ref_jg + h);
-	hi = ldr(ix.ref_jg + h + 1);
+	const uint32_t k = (uint32_t)h & 3u;
+	const uint32_t *r = ix.xdir + (h >> 2) * 5 + k;
+	lo = ldr(r);
+	hi = ldr(r + 1 + (k == 3u));                     // word 4 of the record is the SNP directory: skip it
 }
 __device__ __forceinline__ void ref_lo_bucket(const DevIndex &ix, uint32_t lo32, uint32_t &s, uint32_t &e)
 {
@@ -187,8 +197,9 @@ __device__ __forceinline__ uint64_t snp_scan_lo40(const DevIndex &ix, uint32_t l
 __device__ __forceinline__ void snp_block30(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
 	const uint64_t h = kmer >> 34;
-	lo = ldr(ix.snp_jg30 + h);
-	hi = ldr(ix.snp_jg30 + h + 1);
+	const uint32_t *r = ix.xdir + h * 5 + 4;
+	lo = ldr(r);
+	hi = ldr(r + 5);
 }
 __device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
 {

@@ -270,6 +270,26 @@ __global__ void __launch_bounds__(256) k_parse_snp(const uint4 *raw, uint64_t fi
 	if (err) { atomicAdd(&po->errors, 1ull); atomicCAS(&po->first_error_kind, 0u, err); }
 }
 
+// combined directory (vgb_common.cuh): words 0..3 of record p = ref_jg[4p .. 4p+3]; record 2^30 holds the sentinel ref_jg[2^32]
+__global__ void __launch_bounds__(256) k_xdir_ref(const uint32_t *jg, uint32_t *x)
+{
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p > (1ull << 30)) return;
+	uint32_t *r = x + 5 * p;
+	if (p < (1ull << 30)) {
+		const uint4 a = *reinterpret_cast<const uint4 *>(jg + 4 * p);
+		r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+	} else {
+		r[0] = jg[4 * p]; r[1] = 0; r[2] = 0; r[3] = 0;
+	}
+}
+// word 4 of record p = snp_jg30[p], p in [0, 2^30]
+__global__ void __launch_bounds__(256) k_xdir_snp(const uint32_t *sjg30, uint32_t *x)
+{
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p <= (1ull << 30)) x[5 * p + 4] = sjg30[p];
+}
+
 __global__ void __launch_bounds__(256) k_snp_scan_layout(const SnpEntry *snp, uint64_t n, uint64_t stride, uint64_t *scan)
 {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +404,14 @@ static int stream_records(vgb_ctx *c, const uint8_t *src, uint64_t n_rec, uint32
 
 static uint64_t rd_kmer(const uint8_t *rec) { uint64_t k; memcpy(&k, rec, 8); return k; }
 
+// release a device allocation that dev_alloc registered with the context
+static void free_owned(vgb_ctx *c, void *p)
+{
+	for (int i = 0; i < c->n_owned; i++)
+		if (c->owned[i] == p) { c->owned[i] = c->owned[--c->n_owned]; break; }
+	cudaFree(p);
+}
+
 int index_upload(vgb_ctx *c, const vgb_index_view *v)
 {
 	if (c->have_index) return set_err(c, VGB_E_ARG, "an index is already resident in this context");
@@ -404,7 +432,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	RefEntry *d_ref = nullptr, *d_by_lo = nullptr; uint32_t *d_jg = nullptr, *d_jg_lo = nullptr; uint32_t *d_aux = nullptr;
 	if ((rc = dev_alloc(c, &d_ref, v->n_ref))) return rc;
 	if ((rc = dev_alloc(c, &d_by_lo, v->n_ref))) return rc;
-	if ((rc = dev_alloc(c, &d_jg, (1ull << 32) + 1))) return rc;
+	if ((rc = dev_alloc(c, &d_jg, (1ull << 32) + 1))) return rc;                 // temporary: folded into xdir below
 	if ((rc = dev_alloc(c, &d_jg_lo, (1ull << 32) + 1))) return rc;
 	VGB_CUDA(c, cudaMemsetAsync(d_jg_lo, 0, ((1ull << 32) + 1) * 4, c->stream));
 	if ((rc = dev_alloc(c, &d_aux, v->n_ref_aux * AUX_COLS))) return rc;
@@ -421,12 +449,18 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	// bucket sizes -> bucket starts (in place), then scatter; the cursor array ends up holding bucket ends
 	if ((rc = exclusive_scan_u32(c, d_jg_lo, d_jg_lo, 1ull << 32, d_tmp, nullptr))) return rc;
 	k_scatter_by_lo<<<(unsigned)((1ull << 32) / 256), 256, 0, c->stream>>>(d_ref, d_jg, d_jg_lo, d_by_lo);
-	c->launches++;
+	// first half of the combined directory (vgb_common.cuh); the 16 GiB jumpgate itself is released before the SNP side allocates
+	uint32_t *d_xdir = nullptr;
+	if ((rc = dev_alloc(c, &d_xdir, ((1ull << 30) + 1) * 5))) return rc;
+	k_xdir_ref<<<(unsigned)(((1ull << 30) + 1 + 255) / 256), 256, 0, c->stream>>>(d_jg, d_xdir);
+	c->launches += 2;
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	free_owned(c, d_jg);
 	ParseOut po;
 	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "reference dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	if (po.max_pos >= amb_lo) return set_err(c, VGB_E_INDEX, "reference dictionary: %s", parse_err_text(2));
-	ix.ref = d_ref; ix.n_ref = v->n_ref; ix.ref_jg = d_jg; ix.ref_aux = d_aux; ix.n_ref_aux = (uint32_t)v->n_ref_aux; ix.amb_lo = amb_lo;
+	ix.ref = d_ref; ix.n_ref = v->n_ref; ix.ref_aux = d_aux; ix.n_ref_aux = (uint32_t)v->n_ref_aux; ix.amb_lo = amb_lo;
 	ix.ref_by_lo = d_by_lo; ix.ref_jg_lo = d_jg_lo;
 
 	// ---- SNP dictionary + static pileup ----
@@ -435,7 +469,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	SnpEntry *d_snp = nullptr; uint32_t *d_sjg, *d_sjg30, *d_sap, *d_lw; uint8_t *d_sai;
 	if ((rc = dev_alloc(c, &d_snp, v->n_snp))) return rc;
 	if ((rc = dev_alloc(c, &d_sjg, (1ull << 24) + 1))) return rc;
-	if ((rc = dev_alloc(c, &d_sjg30, (1ull << 30) + 1))) return rc;
+	if ((rc = dev_alloc(c, &d_sjg30, (1ull << 30) + 1))) return rc;             // temporary: folded into xdir below
 	VGB_CUDA(c, cudaMemsetAsync(d_sjg30, 0xFF, ((1ull << 30) + 1) * 4, c->stream));
 	if ((rc = dev_alloc(c, &d_sap, v->n_snp_aux * AUX_COLS))) return rc;
 	if ((rc = dev_alloc(c, &d_sai, v->n_snp_aux * AUX_COLS))) return rc;
@@ -457,7 +491,12 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	}
 	if ((rc = fill_jumpgate(c, d_sjg, 24, (uint32_t)v->n_snp, d_tmp))) return rc;
 	if ((rc = fill_jumpgate(c, d_sjg30, 30, (uint32_t)v->n_snp, d_tmp))) return rc;
-	ix.snp_jg30 = d_sjg30;
+	// second half of the combined directory; the separate array is not needed any more
+	k_xdir_snp<<<(unsigned)(((1ull << 30) + 1 + 255) / 256), 256, 0, c->stream>>>(d_sjg30, d_xdir);
+	c->launches++;
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	free_owned(c, d_sjg30);
+	ix.xdir = d_xdir;
 	{
 		// residue-major LO40 column for the strided scan
 		const uint64_t stride = (v->n_snp + SNP_STRIDE - 1) / SNP_STRIDE + 1;
