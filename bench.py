@@ -32,7 +32,7 @@ REC_ID_WIDTH = 9
 # DRAM bytes one k_geno8 launch really moves (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
 # this workload at 2 M reads per launch: profiles/r01_k_geno8_ncu_full.csv); a number taken under the profiler, so it is a
 # constant here, not something measured in the timed run
-NCU_TRAFFIC = {"bytes": 3.519826e9 + 57.766400e6, "reads_per_launch": 2_000_000, "source": "profiles/r01_k_geno8_ncu_full.csv"}
+NCU_TRAFFIC = {"bytes": 3.120863e9 + 55.968512e6, "reads_per_launch": 2_000_000, "source": "profiles/r01_k_geno8_ncu_full.csv"}
 S1_SUB_RATE, S1_LOWQ_PROB, S1_LOWQ_CHARS = 0.005, 0.25, 4
 
 
