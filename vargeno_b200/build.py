@@ -75,6 +75,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         if force or _newer(HOST_BIN, host_srcs + hdrs + [LIB]):
             _run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", HOST_BIN] + host_srcs +
                  ["-L" + HERE, "-lvgb200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz"])
+    # stand-alone measurement tool (profiles/r01_sector_probe.md); not linked into anything
+    probe_src = os.path.join(HERE, "tools", "probes", "sector_probe.cu")
+    probe_bin = os.path.join(HERE, "tools", "probes", "sector_probe")
+    if os.path.exists(probe_src) and (force or _newer(probe_bin, [probe_src])):
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-o", probe_bin, probe_src])
     return LIB
 
 
