@@ -281,7 +281,7 @@ def run_ours(args):
             "host_binding": numa,
             "setup_s": setup_s,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     g.dfree(d_reads)
     g.close()
     if world > 1:
@@ -424,10 +424,29 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of this process, on the real stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    # Libraries print to fd 1 on their own (NCCL's "NCCL version ..." banner at communicator set-up): everything but the
+    # result line goes to stderr, so that stdout carries exactly one JSON line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
