@@ -195,7 +195,7 @@ def test_format_violations_are_loud(cache):
 
 
 def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
-    """Reads of 288+ bases (more than 8 k-mers) and reads with more hit contexts than the 8-lane kernel keeps in shared
+    """Reads of 288+ bases (more than 8 k-mers) and reads with more hit contexts than the group kernels (4 or 8 lanes per read) keep in shared
     memory are handed to the warp-per-read kernel; results must not depend on which kernel handled a read."""
     from vargeno_b200.geno import Genotyper
     from vargeno_b200.tools import synth
@@ -215,7 +215,7 @@ def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
         parts.append(synth.simulate_reads(g0, haps, n, L, seed=77 + L, sub_rate=0.01, lowq_prob=0.7, lowq_chars=31, first_id=first))
         first += n
     # reverse-strand 150 bp reads over the 6-copy repeat family, all leading qualities low: the forward pass finds nothing, the
-    # retry finds 6 positions per k-mer (24 exact contexts) plus neighbours -> more than the 8-lane kernel keeps
+    # retry finds 6 positions per k-mer (24 exact contexts) plus neighbours -> more than the group kernels keep
     gb = datasets.adv_b_genome()
     rs = np.array([o + d for (_, _, ci, o, l) in gb.repeat_copies if l == 250 for d in (0, 7, 33, 64, 100)] * 4, dtype=np.int64)
     assert rs.size >= 100
@@ -242,7 +242,7 @@ def test_long_reads_and_context_overflow_take_the_deferred_path(cache):
     for k in ("reads", "passes", "placed", "exact_lookups", "nbr_query_lookups", "nbr_scan_reads", "events", "pileup_incr", "big_kmers"):
         assert st[k] == ost[k], k
     assert int(want["n_ref"].max()) + int(want["n_snp"].max()) > 24, "the set should contain reads beyond the shared-memory context budget"
-    # short reads (<= 8 k-mers) whose RETRY pass overflows the budget: the 8-lane kernel has already run and accounted for their
+    # short reads (<= 8 k-mers) whose RETRY pass overflows the budget: the 4-lane kernel has already run and accounted for their
     # forward pass and hands over only the retry (bit 31 of the deferred-list entry)
     short = np.arange(want.size) >= n_before_retry_set
     n_retry_overflow = int(np.count_nonzero(short & (want["passes"] == 2) & (want["n_ref"].astype(int) + want["n_snp"].astype(int) > 24)))
