@@ -89,3 +89,24 @@ def test_record_larger_than_chunk_is_an_error(tmp_path):
 def test_missing_file_is_an_error(tmp_path):
     p = _run(str(tmp_path / "nope.fq"), 4096)
     assert p.returncode != 0 and "cannot open" in p.stderr
+
+
+def test_parallel_pread_gives_the_same_chunks(tmp_path):
+    """Large reads of a plain file are split over several pread()s running in parallel (VGB_READ_THREADS): same chunks, byte for
+    byte, as the single-threaded reader."""
+    import os
+    vb.build()
+    block = _fastq(2000, seed=9)
+    f = tmp_path / "big.fq"
+    with open(f, "wb") as out:
+        for _ in range(60):
+            out.write(block)                    # ~45 MB
+    outs = []
+    for t in ("1", "5"):
+        env = dict(os.environ, VGB_READ_THREADS=t)
+        p = subprocess.run([vb.HOST_BIN, "fastq-chunks", str(f), "--chunk-bytes", str(20 << 20)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        outs.append(p.stdout)
+    assert outs[0] == outs[1]
+    assert outs[0].strip().splitlines()[-1].startswith("total %d bytes" % (60 * len(block)))
