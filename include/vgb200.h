@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VGB_ABI_VERSION 1
+#define VGB_ABI_VERSION 2
 
 typedef struct vgb_ctx vgb_ctx;
 
@@ -109,6 +109,8 @@ typedef struct {
 	uint64_t chunks, chunk_bytes;
 	double   gpu_ms_parse, gpu_ms_geno;   /* CUDA-event time of the K1 kernels and of the fused per-read kernel */
 	uint64_t kernel_launches;
+	uint64_t freq_wrap_reads;    /* reads with more than 255 votes for one position: the reference's uint8 counter wraps there
+	                                (src/qv.cc:57-93); never silently used -- vgb_sync fails with VGB_E_OVERFLOW */
 } vgb_stats;
 
 /* ---- life cycle ---- */
@@ -117,6 +119,10 @@ int  vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg);
 void vgb_ctx_destroy(vgb_ctx *ctx);
 const char *vgb_last_error(const vgb_ctx *ctx);   /* ctx may be NULL: error of the last failed vgb_ctx_create */
 int  vgb_nccl_unique_id(void *out128);            /* ncclGetUniqueId through the dlopen'ed libnccl */
+/* Joins a context that was created with world_size == 1 to a communicator afterwards (collective: every rank calls it).
+ * Lets a host create and load all of its contexts first and start the collective NCCL initialisation only when every
+ * rank got that far -- a rank that fails early can then not leave the others blocked in ncclCommInitRank. */
+int  vgb_comm_init(vgb_ctx *ctx, int32_t world_size, int32_t rank, const void *nccl_unique_id);
 
 /* ---- index: replaces the dictionary / jumpgate / pileup construction of src/qv.cc:519-695 and the
  *      Bloom filter loads of src/qv.cc:2140-2144 ---- */

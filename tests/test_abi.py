@@ -24,7 +24,7 @@ def test_header_and_library_agree(lib):
     assert declared == set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vgb_abi_version() == 1
+    assert lib.vgb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -41,8 +41,8 @@ READ_RESULT = np.dtype([("flags", "<u4"), ("target", "<u4"), ("freq", "<u2"), ("
 STATS = np.dtype([(k, "<u8") for k in ("reads", "skipped_n", "passes", "placed", "exact_lookups", "nbr_query_lookups",
                                        "nbr_scan_reads", "bf_probes", "lowq_kmers", "events", "pileup_incr", "big_kmers",
                                        "bad_records", "chunks", "chunk_bytes")] +
-                 [("gpu_ms_parse", "<f8"), ("gpu_ms_geno", "<f8"), ("kernel_launches", "<u8")])
-assert HIT.itemsize == 32 and READ_RESULT.itemsize == 24 and STATS.itemsize == 18 * 8
+                 [("gpu_ms_parse", "<f8"), ("gpu_ms_geno", "<f8"), ("kernel_launches", "<u8"), ("freq_wrap_reads", "<u8")])
+assert HIT.itemsize == 32 and READ_RESULT.itemsize == 24 and STATS.itemsize == 19 * 8
 
 # every symbol include/vgb200.h declares (tests check the library exports all of them)
 SYMBOLS = ["vgb_abi_version", "vgb_ctx_create", "vgb_ctx_destroy", "vgb_last_error", "vgb_nccl_unique_id", "vgb_index_upload",
@@ -51,7 +51,7 @@ SYMBOLS = ["vgb_abi_version", "vgb_ctx_create", "vgb_ctx_destroy", "vgb_last_err
            "vgb_call", "vgb_counter_device_ptr", "vgb_get_stats", "vgb_probe_bench", "vgb_random_sector_bench",
            "vgb_synth_reads_device", "vgb_device_alloc", "vgb_device_free", "vgb_memcpy_d2h", "vgb_memcpy_h2d",
            "vgb_build_index_device", "vgb_free_index_device", "vgb_index_upload_device", "vgb_synth_genome_device",
-           "vgb_memcpy_d2d", "vgb_memset_device"]
+           "vgb_memcpy_d2d", "vgb_memset_device", "vgb_comm_init"]
 
 _lib = None
 
@@ -99,11 +99,12 @@ def load():
         "vgb_synth_genome_device": (i32, [vp, vp, vp, vp, u32, u64]),
         "vgb_memcpy_d2d": (i32, [vp, vp, vp, u64]),
         "vgb_memset_device": (i32, [vp, vp, i32, u64]),
+        "vgb_comm_init": (i32, [vp, i32, i32, vp]),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)           # AttributeError if the library does not export what the header declares
         fn.restype, fn.argtypes = sig[name]
-    if L.vgb_abi_version() != 1:
+    if L.vgb_abi_version() != 2:
         raise ImportError("libvgb200.so ABI version mismatch")
     _lib = L
     return L

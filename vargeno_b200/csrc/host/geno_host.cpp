@@ -475,8 +475,11 @@ int rewrite_vcf(const std::string &vcf_in, const std::string &vcf_out, const std
 		else { col.push_back(join(fmt, ':')); col.push_back(join(smp, ':')); }
 		out << join(col, '\t') << '\n';
 	}
+	out.flush();
+	const bool ok = out.good();
 	out.close();
-	return out.good() || true ? VGB_OK : VGB_E_ARG;
+	if (!ok || out.fail()) { err = "writing the output VCF failed (disk full or I/O error)"; return VGB_E_ARG; }
+	return VGB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -493,7 +496,8 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 	if (!ix.open(prefix, err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
 	fprintf(stderr, "Initializing...\n");
 
-	// one context per GPU, created and loaded concurrently (NCCL rank initialisation is collective)
+	// one context per GPU, created and loaded concurrently.  The collective NCCL initialisation starts only after every
+	// rank has its context and its index (vgb_comm_init): a rank that fails early cannot leave the others blocked
 	unsigned char uid[128];
 	if (n_gpus > 1 && vgb_nccl_unique_id(uid) != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", vgb_last_error(nullptr)); return EXIT_FAILURE; }
 	std::vector<vgb_ctx *> ctxs(n_gpus, nullptr);
@@ -504,8 +508,8 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 		for (int r = 0; r < n_gpus; r++)
 			th.emplace_back([&, r]() {
 				vgb_config cfg{};
-				cfg.device = r; cfg.world_size = n_gpus; cfg.rank = r; cfg.flags = 0;
-				cfg.nccl_unique_id = n_gpus > 1 ? uid : nullptr;
+				cfg.device = r; cfg.world_size = 1; cfg.rank = 0; cfg.flags = 0;
+				cfg.nccl_unique_id = nullptr;
 				cfg.max_chunk_bytes = chunk_bytes;
 				rcs[r] = vgb_ctx_create(&ctxs[r], &cfg);
 				if (rcs[r]) { errs[r] = vgb_last_error(nullptr); return; }
@@ -520,6 +524,18 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 			for (auto c : ctxs) vgb_ctx_destroy(c);
 			return EXIT_FAILURE;
 		}
+	if (n_gpus > 1) {
+		std::vector<std::thread> th;
+		for (int r = 0; r < n_gpus; r++)
+			th.emplace_back([&, r]() { rcs[r] = vgb_comm_init(ctxs[r], n_gpus, r, uid); if (rcs[r]) errs[r] = vgb_last_error(ctxs[r]); });
+		for (auto &t : th) t.join();
+		for (int r = 0; r < n_gpus; r++)
+			if (rcs[r]) {
+				fprintf(stderr, "vargeno-b200: GPU %d: %s\n", r, errs[r].c_str());
+				for (auto c : ctxs) vgb_ctx_destroy(c);
+				return EXIT_FAILURE;
+			}
+	}
 	const double t_load = secs(t0);
 	fprintf(stderr, "Processing...\n");
 

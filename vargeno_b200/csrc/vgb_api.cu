@@ -65,23 +65,16 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 	if (c->max_chunk_bytes > 0xFFFFFF00ull) { delete c; return set_err(nullptr, VGB_E_ARG, "max_chunk_bytes must stay below 4 GiB (32-bit line offsets)"); }
 	c->max_chunk_bytes = (c->max_chunk_bytes + 4095) & ~4095ull;
 #define CK(call) do { if ((e = (call)) != cudaSuccess) { set_err(nullptr, VGB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e)); vgb_ctx_destroy(c); return VGB_E_CUDA; } } while (0)
-	{
-		// the probes of this path want single 32-byte sectors; ask L2 not to fetch 64 B per miss (profiles/r01_summary.md).
-		// VGB_L2_FETCH=64|128 restores a larger granularity for A/B measurements.
-		size_t gran = 32;
-		if (const char *e2 = getenv("VGB_L2_FETCH")) gran = (size_t)atoi(e2);
-		if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-	}
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
 	CK(cudaMalloc((void **)&c->d_stats, sizeof(DevStats)));
-	CK(cudaMemset(c->d_stats, 0, sizeof(DevStats)));
+	CK(vgb::memset_sync(c, c->d_stats, 0, sizeof(DevStats)));
 	CK(cudaMalloc((void **)&c->d_tables, (64 * 64 * 3 + 127) * sizeof(double)));
 	{
 		std::vector<double> t(64 * 64 * 3 + 127);
 		build_call_tables(t.data(), t.data() + 64 * 64 * 3);
-		CK(cudaMemcpy(c->d_tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+		CK(vgb::copy_sync(c, c->d_tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
 	}
 	const uint64_t nblk = c->max_chunk_bytes / 4096 + 2;
 	for (int s = 0; s < 2; s++) {
@@ -92,7 +85,7 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 		CK(cudaMalloc((void **)&k.d_defer, (c->max_chunk_bytes / 8 + 16) * 4));
 		CK(cudaMalloc((void **)&k.d_defer2, (c->max_chunk_bytes / 8 + 16) * 4));
 		CK(cudaMalloc((void **)&k.d_meta, 64));
-		CK(cudaMemset(k.d_meta, 0, 64));
+		CK(vgb::memset_sync(c, k.d_meta, 0, 64));
 		CK(cudaEventCreateWithFlags(&k.copied, cudaEventDisableTiming));
 		CK(cudaEventCreate(&k.done));
 		CK(cudaEventCreate(&k.t0));
@@ -106,6 +99,19 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 	}
 	*out = c;
 	return VGB_OK;
+}
+
+int vgb_comm_init(vgb_ctx *c, int32_t world_size, int32_t rank, const void *uid)
+{
+	if (!c) return VGB_E_ARG;
+	if (world_size < 2 || rank < 0 || rank >= world_size || !uid) return set_err(c, VGB_E_ARG, "bad world_size / rank / unique id");
+	if (c->nccl_comm || c->cfg.world_size != 1) return set_err(c, VGB_E_ARG, "context already belongs to a communicator");
+	cudaSetDevice(c->device);
+	memcpy(c->uid, uid, 128);
+	c->cfg.world_size = world_size; c->cfg.rank = rank; c->cfg.nccl_unique_id = c->uid;
+	const int rc = nccl_init(c);
+	if (rc) { c->cfg.world_size = 1; c->cfg.rank = 0; c->cfg.nccl_unique_id = nullptr; }
+	return rc;
 }
 
 void vgb_ctx_destroy(vgb_ctx *c)
@@ -123,6 +129,7 @@ void vgb_ctx_destroy(vgb_ctx *c)
 		if (k.done) cudaEventDestroy(k.done);
 		if (k.t0) cudaEventDestroy(k.t0);
 		if (k.t1) cudaEventDestroy(k.t1);
+		if (k.g0) cudaEventDestroy(k.g0);
 	}
 	cudaFree(c->d_stats); cudaFree(c->d_tables); cudaFree(c->d_trace);
 	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -153,10 +160,10 @@ int vgb_fetch_sites(vgb_ctx *c, uint32_t *pos, uint8_t *code, uint8_t *rf, uint8
 	if (n != c->ix.n_sites) return set_err(c, VGB_E_ARG, "n_sites mismatch");
 	cudaSetDevice(c->device);
 	if (n == 0) return VGB_OK;
-	if (pos) VGB_CUDA(c, cudaMemcpy(pos, c->d_site_pos, n * 4, cudaMemcpyDeviceToHost));
-	if (code) VGB_CUDA(c, cudaMemcpy(code, c->ix.site_code, n, cudaMemcpyDeviceToHost));
-	if (rf) VGB_CUDA(c, cudaMemcpy(rf, c->d_site_rf, n, cudaMemcpyDeviceToHost));
-	if (af) VGB_CUDA(c, cudaMemcpy(af, c->d_site_af, n, cudaMemcpyDeviceToHost));
+	if (pos) VGB_CUDA(c, vgb::copy_sync(c, pos, c->d_site_pos, n * 4, cudaMemcpyDeviceToHost));
+	if (code) VGB_CUDA(c, vgb::copy_sync(c, code, c->ix.site_code, n, cudaMemcpyDeviceToHost));
+	if (rf) VGB_CUDA(c, vgb::copy_sync(c, rf, c->d_site_rf, n, cudaMemcpyDeviceToHost));
+	if (af) VGB_CUDA(c, vgb::copy_sync(c, af, c->d_site_af, n, cudaMemcpyDeviceToHost));
 	return VGB_OK;
 }
 
@@ -226,7 +233,7 @@ static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_
 				vgb_read_result *nt = nullptr;
 				VGB_CUDA(c, cudaStreamSynchronize(c->stream));       // earlier chunks still write the old buffer
 				VGB_CUDA(c, cudaMalloc((void **)&nt, cap * sizeof(vgb_read_result)));
-				if (c->trace_n) VGB_CUDA(c, cudaMemcpy(nt, c->d_trace, c->trace_n * sizeof(vgb_read_result), cudaMemcpyDeviceToDevice));
+				if (c->trace_n) VGB_CUDA(c, vgb::copy_sync(c, nt, c->d_trace, c->trace_n * sizeof(vgb_read_result), cudaMemcpyDeviceToDevice));
 				cudaFree(c->d_trace);
 				c->d_trace = nt; c->trace_cap = cap;
 			}
@@ -274,11 +281,11 @@ int vgb_sync(vgb_ctx *c)
 	uint32_t bits = 0;
 	for (int s = 0; s < 2; s++) {
 		uint32_t meta[6] = { 0, 0, 0, 0, 0, 0 };
-		VGB_CUDA(c, cudaMemcpy(meta, c->chunk[s].d_meta, 24, cudaMemcpyDeviceToHost));
+		VGB_CUDA(c, vgb::copy_sync(c, meta, c->chunk[s].d_meta, 24, cudaMemcpyDeviceToHost));
 		bits |= meta[3] | meta[5];
 	}
 	DevStats st;
-	VGB_CUDA(c, cudaMemcpy(&st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+	VGB_CUDA(c, vgb::copy_sync(c, &st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
 	c->sticky_format |= bits;
 	if (c->sticky_format || st.bad_records)
 		return set_err(c, VGB_E_FORMAT, "FASTQ input violates the contract:%s%s%s (%llu bad records)",
@@ -287,6 +294,8 @@ int vgb_sync(vgb_ctx *c)
 		               (c->sticky_format & 4) ? " too many lines for max_chunk_bytes;" : "", st.bad_records);
 	if (st.overflow_reads)
 		return set_err(c, VGB_E_OVERFLOW, "%llu reads produced more than 2000 hit contexts per dictionary (the reference overflows its arrays, src/qv.cc:709,728-729)", st.overflow_reads);
+	if (st.freq_wrap_reads)
+		return set_err(c, VGB_E_OVERFLOW, "%llu reads gave one position more than 255 votes (the reference's uint8 vote counter wraps there, src/qv.cc:57-93; results for these reads would differ)", st.freq_wrap_reads);
 	return VGB_OK;
 }
 
@@ -296,9 +305,9 @@ int vgb_reset_counts(vgb_ctx *c)
 	cudaSetDevice(c->device);
 	VGB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
-	VGB_CUDA(c, cudaMemset(c->d_stats, 0, sizeof(DevStats)));
-	if (c->have_index && c->ix.n_sites) VGB_CUDA(c, cudaMemset(c->ix.cnt, 0, 2 * c->ix.n_sites * 4));
-	for (int s = 0; s < 2; s++) VGB_CUDA(c, cudaMemset(c->chunk[s].d_meta, 0, 64));
+	VGB_CUDA(c, vgb::memset_sync(c, c->d_stats, 0, sizeof(DevStats)));
+	if (c->have_index && c->ix.n_sites) VGB_CUDA(c, vgb::memset_sync(c, c->ix.cnt, 0, 2 * c->ix.n_sites * 4));
+	for (int s = 0; s < 2; s++) VGB_CUDA(c, vgb::memset_sync(c, c->chunk[s].d_meta, 0, 64));
 	c->trace_n = 0; c->sticky_format = 0;
 	c->chunks = c->chunk_bytes = 0; c->ms_parse = c->ms_geno = 0; c->launches = 0;
 	return VGB_OK;
@@ -312,7 +321,7 @@ int vgb_fetch_read_results(vgb_ctx *c, vgb_read_result *out, uint64_t cap, uint6
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	*n = c->trace_n;
 	const uint64_t m = std::min(cap, c->trace_n);
-	if (out && m) VGB_CUDA(c, cudaMemcpy(out, c->d_trace, m * sizeof(vgb_read_result), cudaMemcpyDeviceToHost));
+	if (out && m) VGB_CUDA(c, vgb::copy_sync(c, out, c->d_trace, m * sizeof(vgb_read_result), cudaMemcpyDeviceToHost));
 	return VGB_OK;
 }
 
@@ -366,7 +375,7 @@ int vgb_get_stats(vgb_ctx *c, vgb_stats *out)
 	collect_times(c, 0);
 	collect_times(c, 1);
 	DevStats st;
-	VGB_CUDA(c, cudaMemcpy(&st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+	VGB_CUDA(c, vgb::copy_sync(c, &st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
 	memset(out, 0, sizeof(*out));
 	out->reads = st.reads; out->skipped_n = st.skipped_n; out->passes = st.passes; out->placed = st.placed;
 	out->exact_lookups = st.exact_lookups; out->nbr_query_lookups = st.nbr_query_lookups; out->nbr_scan_reads = st.nbr_scan_reads;
@@ -374,6 +383,7 @@ int vgb_get_stats(vgb_ctx *c, vgb_stats *out)
 	out->big_kmers = st.big_kmers; out->bad_records = st.bad_records;
 	out->chunks = c->chunks; out->chunk_bytes = c->chunk_bytes;
 	out->gpu_ms_parse = c->ms_parse; out->gpu_ms_geno = c->ms_geno; out->kernel_launches = c->launches;
+	out->freq_wrap_reads = st.freq_wrap_reads;
 	return VGB_OK;
 }
 
@@ -459,7 +469,7 @@ int vgb_memcpy_d2h(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
-	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	VGB_CUDA(c, vgb::copy_sync(c, dst, src, bytes, cudaMemcpyDeviceToHost));
 	return VGB_OK;
 }
 
@@ -467,7 +477,7 @@ int vgb_memcpy_d2d(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
 {
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
-	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+	VGB_CUDA(c, vgb::copy_sync(c, dst, src, bytes, cudaMemcpyDeviceToDevice));
 	return VGB_OK;
 }
 
@@ -475,7 +485,7 @@ int vgb_memset_device(vgb_ctx *c, void *dst, int value, uint64_t bytes)
 {
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
-	VGB_CUDA(c, cudaMemset(dst, value, bytes));
+	VGB_CUDA(c, vgb::memset_sync(c, dst, value, bytes));
 	return VGB_OK;
 }
 
@@ -483,7 +493,7 @@ int vgb_memcpy_h2d(vgb_ctx *c, void *dst, const void *src, uint64_t bytes)
 {
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
-	VGB_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+	VGB_CUDA(c, vgb::copy_sync(c, dst, src, bytes, cudaMemcpyHostToDevice));
 	return VGB_OK;
 }
 

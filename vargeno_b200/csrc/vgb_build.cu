@@ -296,7 +296,7 @@ int build_index_device(vgb_ctx *c, const uint8_t *d_genome, uint64_t genome_len,
 		std::vector<SnpLine> h(n_snp_lines);
 		for (uint64_t i = 0; i < n_snp_lines; i++) { h[i].pos0 = snp_pos0[i]; h[i].code = snp_code[i]; h[i].rf = snp_rf[i]; h[i].af = snp_af[i]; h[i].pad = 0; }
 		if ((rc = dev_alloc(c, &lines, n_snp_lines, false))) return rc;
-		if (n_snp_lines) VGB_CUDA(c, cudaMemcpy(lines, h.data(), n_snp_lines * sizeof(SnpLine), cudaMemcpyHostToDevice));
+		if (n_snp_lines) VGB_CUDA(c, vgb::copy_sync(c, lines, h.data(), n_snp_lines * sizeof(SnpLine), cudaMemcpyHostToDevice));
 	}
 	const uint64_t n_sk = n_snp_lines * 32;
 	if (n_sk >= 0xFFFFFFF0ull) return set_err(c, VGB_E_INDEX, "too many SNP k-mers");

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 			}
 			if (bad) {
 				w_bad++;
-				if (lane == 0) atomicOr(&a.meta[3], 2u);
+				if (lane == 0) atomicOr(&a.meta[5], 2u);
 				if (a.trace && lane == 0) { res.flags = VGB_RF_SKIPPED; a.trace[r] = res; }
 				continue;
 			}
@@ -494,10 +494,6 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 #include "vgb_geno8.inl"
 
 typedef void (*geno_kernel_t)(const GenoArgs);
-static geno_kernel_t g_warp_kernel = nullptr;
-static geno_kernel_t g_grp_kernel[2][2] = {};        // [lanes per read: 0 = 4, 1 = 8][trace]
-static uint32_t g_grp_grid[2] = {};
-static bool g_use_quad = true;
 static size_t grp_smem_bytes(int G) { const size_t R = 32 / G; return sizeof(OctSmem) * GW * R + GW * 16 * sizeof(uint32_t) + (G == 4 ? sizeof(Pend<4>) : sizeof(Pend<8>)) * GW * 2 * R; }
 
 template <int G>
@@ -520,12 +516,14 @@ int geno_prepare(vgb_ctx *c)
 	if (const char *e = getenv("VGB_GENO4_MINB")) minb4 = atoi(e);
 	const char *kk = getenv("VGB_GENO_KERNEL");
 	const bool warp_only = kk && !strcmp(kk, "warp");
-	g_use_quad = !(kk && !strcmp(kk, "oct"));
+	c->use_quad = !(kk && !strcmp(kk, "oct"));
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
-	g_warp_kernel = k;
-	pick_group_kernels<4>(minb4, g_grp_kernel[0][0], g_grp_kernel[0][1]);
-	pick_group_kernels<8>(minb8, g_grp_kernel[1][0], g_grp_kernel[1][1]);
-	if (warp_only) g_grp_kernel[0][0] = g_grp_kernel[0][1] = g_grp_kernel[1][0] = g_grp_kernel[1][1] = nullptr;
+	geno_kernel_t grp[2][2];
+	pick_group_kernels<4>(minb4, grp[0][0], grp[0][1]);
+	pick_group_kernels<8>(minb8, grp[1][0], grp[1][1]);
+	if (warp_only) grp[0][0] = grp[0][1] = grp[1][0] = grp[1][1] = nullptr;
+	c->warp_kernel = (void *)k;
+	for (int i = 0; i < 2; i++) for (int t = 0; t < 2; t++) c->grp_kernel[i][t] = (void *)grp[i][t];
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
 	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -534,10 +532,10 @@ int geno_prepare(vgb_ctx *c)
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
 	for (int gi = 0; gi < 2 && !warp_only; gi++) {
 		const size_t sm = grp_smem_bytes(gi ? 8 : 4);   // hit contexts + one row of counters per warp + the warp's parked reads
-		for (int t = 0; t < 2; t++) VGB_CUDA(c, cudaFuncSetAttribute(g_grp_kernel[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-		VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_grp_kernel[gi][0], GW * 32, sm));
+		for (int t = 0; t < 2; t++) VGB_CUDA(c, cudaFuncSetAttribute(grp[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, grp[gi][0], GW * 32, sm));
 		if (occ < 1) occ = 1;
-		g_grp_grid[gi] = (uint32_t)(c->sm_count * occ);
+		c->grp_grid[gi] = (uint32_t)(c->sm_count * occ);
 	}
 	if (!c->d_spill) {
 		Event *sp = nullptr;
@@ -563,22 +561,23 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.defer = ck.d_defer;
 	a.klist = nullptr;
 	a.kdefer = ck.d_defer2;
-	const int t = a.trace ? 1 : 0;   // per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernels carry none of it
-	if (g_grp_kernel[1][0]) {
+	const geno_kernel_t warp_kernel = (geno_kernel_t)c->warp_kernel;
+	const geno_kernel_t grp4 = (geno_kernel_t)c->grp_kernel[0][a.trace ? 1 : 0], grp8 = (geno_kernel_t)c->grp_kernel[1][a.trace ? 1 : 0];   // per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernels carry none of it
+	if (grp8) {
 		// 4 lanes per read (up to 4 k-mers: 128..159 bases), then 8 lanes per read for what it handed over (5..8 k-mers), then
 		// one warp per read for the rest (longer reads, more hit contexts than the group kernels keep in shared memory)
-		if (g_use_quad) {
-			g_grp_kernel[0][t]<<<g_grp_grid[0], GW * 32, grp_smem_bytes(4), c->stream>>>(a);
+		if (c->use_quad) {
+			grp4<<<c->grp_grid[0], GW * 32, grp_smem_bytes(4), c->stream>>>(a);
 			a.klist = ck.d_defer2;
 			c->launches++;
 		}
 		a.kdefer = nullptr;
-		g_grp_kernel[1][t]<<<g_grp_grid[1], GW * 32, grp_smem_bytes(8), c->stream>>>(a);
+		grp8<<<c->grp_grid[1], GW * 32, grp_smem_bytes(8), c->stream>>>(a);
 		a.list = ck.d_defer;
-		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches += 2;
 	} else {
-		g_warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches++;
 	}
 	VGB_CUDA(c, cudaGetLastError());

@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				if (run) { atomicAdd(&acc[A_PASSES], 1u); os->st[S_EXACT] = 2u * K; os->st[S_BF] = 2u * os->st[S_LOWQ]; }
 				if (!retry) {
 					atomicAdd(&acc[A_READS], 1u);
-					if (bad) { atomicAdd(&acc[A_BAD], 1u); atomicOr(&a.meta[3], 2u); }
+					if (bad) { atomicAdd(&acc[A_BAD], 1u); atomicOr(&a.meta[5], 2u); }
 					else if (skipped) atomicAdd(&acc[A_SKIPPED], 1u);
 					else {
 						if (process) atomicAdd(&acc[A_PLACED], 1u);

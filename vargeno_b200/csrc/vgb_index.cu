@@ -457,7 +457,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	free_owned(c, d_jg);
 	ParseOut po;
-	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
+	VGB_CUDA(c, vgb::copy_sync(c, &po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "reference dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	if (po.max_pos >= amb_lo) return set_err(c, VGB_E_INDEX, "reference dictionary: %s", parse_err_text(2));
 	ix.ref = d_ref; ix.n_ref = v->n_ref; ix.ref_aux = d_aux; ix.n_ref_aux = (uint32_t)v->n_ref_aux; ix.amb_lo = amb_lo;
@@ -507,7 +507,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 		c->launches++;
 		ix.snp_scan = d_scan; ix.snp_scan_stride = stride;
 	}
-	VGB_CUDA(c, cudaMemcpy(&po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
+	VGB_CUDA(c, vgb::copy_sync(c, &po, d_po, sizeof(po), cudaMemcpyDeviceToHost));
 	if (po.errors) return set_err(c, VGB_E_INDEX, "SNP dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	ix.snp = d_snp; ix.n_snp = v->n_snp; ix.snp_jg = d_sjg; ix.snp_aux_pos = d_sap; ix.snp_aux_info = d_sai; ix.n_snp_aux = (uint32_t)v->n_snp_aux;
 

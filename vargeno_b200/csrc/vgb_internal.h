@@ -61,6 +61,11 @@ struct vgb_ctx {
 	double *d_call_conf = nullptr;
 	uint32_t *d_fetch_ref = nullptr, *d_fetch_alt = nullptr;
 	uint32_t geno_grid = 0;
+	// kernel choice of this context (geno_prepare): instantiation + persistent grid per kernel; nothing process-wide
+	void *warp_kernel = nullptr;
+	void *grp_kernel[2][2] = {};     // [lanes per read: 0 = 4, 1 = 8][trace]
+	uint32_t grp_grid[2] = {};
+	bool use_quad = true;
 
 	// host-side statistics
 	uint64_t chunks = 0, chunk_bytes = 0, launches = 0;
@@ -69,6 +74,7 @@ struct vgb_ctx {
 
 	// NCCL (dlopen)
 	void *nccl_comm = nullptr;
+	unsigned char uid[128] = {};     // copy of the unique id handed to vgb_comm_init
 };
 
 namespace vgb {
@@ -82,6 +88,23 @@ extern thread_local std::string g_create_err;
 		if (e__ != cudaSuccess)                                                                  \
 			return vgb::set_err((c), VGB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
 	} while (0)
+
+// Host-blocking copy / fill ORDERED ON THE CONTEXT'S KERNEL STREAM.  c->stream is created cudaStreamNonBlocking, so the
+// legacy-default-stream forms (cudaMemcpy / cudaMemset) are not ordered with the kernels at all: a pageable H2D copy may
+// return before its last DMA lands and a device memset returns before it ran.  Everything the library copies or clears
+// goes through these two.
+inline cudaError_t copy_sync(vgb_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind)
+{
+	cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	return e;
+}
+inline cudaError_t memset_sync(vgb_ctx *c, void *dst, int value, size_t n)
+{
+	cudaError_t e = cudaMemsetAsync(dst, value, n, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	return e;
+}
 
 template <typename T>
 int dev_alloc(vgb_ctx *c, T **p, uint64_t count, bool own = true)
