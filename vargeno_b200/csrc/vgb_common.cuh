@@ -61,6 +61,14 @@ struct DevIndex {
 	// lo + 11 t, i.e. one residue class mod 11 at consecutive quotients -- stored contiguously here, so the ~23 steps of a
 	// GRCh38-sized block touch ~6 sectors instead of 23:  snp_scan[(r % 11) * snp_scan_stride + r / 11] = LO40(entry r)
 	const uint64_t *snp_scan;   uint64_t snp_scan_stride;
+	// secondary view of the SNP dictionary keyed by LO40 (the lower 20 bases), the twin of ref_by_lo: the 36 upper-half
+	// Hamming-1 neighbours of a k-mer (substitutions in bases 20..31, src/qv.cc:1299-1365 with i >= 40) keep its LO40, so
+	// they are exactly the entries of the bucket "same LO40" whose HI24 differs in one base.  One directory request and,
+	// for the ~30 % of GRCh38-sized buckets that are not empty, one entry sector replace 36 directory probes -- the SNP
+	// Bloom gate is open for ~29 % of all low-quality k-mers at that size (1.12 Gbit filter, 384 M keys).
+	//   snp_by_lo[i] = {kmer lo32, kmer hi32, pos, snp_info | ambig_flag << 8}, grouped by LO40 >> 10, order inside a group unspecified
+	//   snp_dir_lo[q] = END of the group q = LO40 >> 10 (start = end of group q - 1, 0 for q == 0); 2^30 entries
+	const uint4 *snp_by_lo;     const uint32_t *snp_dir_lo;
 	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
 	const uint32_t *ref_bf;     uint64_t ref_bf_bits; uint64_t ref_bf_nw32;
 	const uint32_t *snp_bf;     uint64_t snp_bf_bits; uint64_t snp_bf_nw32;
@@ -142,6 +150,12 @@ __device__ __forceinline__ void ref_lo_bucket(const DevIndex &ix, uint32_t lo32,
 {
 	e = ldr(ix.ref_jg_lo + lo32);
 	s = lo32 ? ldr(ix.ref_jg_lo + lo32 - 1) : 0u;
+}
+__device__ __forceinline__ void snp_lo_bucket(const DevIndex &ix, uint64_t lo40, uint32_t &s, uint32_t &e)
+{
+	const uint32_t q = (uint32_t)(lo40 >> 10);
+	e = ldr(ix.snp_dir_lo + q);
+	s = q ? ldr(ix.snp_dir_lo + q - 1) : 0u;
 }
 __device__ __forceinline__ void snp_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {

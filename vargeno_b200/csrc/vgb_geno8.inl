@@ -231,6 +231,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if ((bfs_bit >> 5) < ix.snp_bf_nw32) bfs_w = ldr(ix.snp_bf + (bfs_bit >> 5));
 			ref_lo_bucket(ix, (uint32_t)kmer, bs, be);     // speculative: used only if the ref Bloom gate is open
 		}
+		const bool rb = gates && ((bfr_w >> (bfr_bit & 31)) & 1u);
+		const bool sb = gates && ((bfs_w >> (bfs_bit & 31)) & 1u);
+		// SNP gate open: bounds of the "same LO40" group that answers the 36 upper-half SNP queries (vgb_common.cuh); issued
+		// here so that it travels under the exact-entry searches
+		uint32_t qs = 0, qe = 0;
+		if (sb) snp_lo_bucket(ix, kmer & 0xFFFFFFFFFFull, qs, qe);
 		// ---- level 2: exact entries (src/qv.cc:840-937) ----
 		if (mine) {
 			uint32_t posx = 0;
@@ -239,8 +245,6 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (f_lo < f_hi && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, f_lo, f_hi, e) >= 0)
 				hit8(ix, os, 1, kmer, e.pos, (uint32_t)(e.key >> 40) & 0xFFFFu, NO_MOD, 32u * ol, ol);
 		}
-		const bool rb = gates && ((bfr_w >> (bfr_bit & 31)) & 1u);
-		const bool sb = gates && ((bfs_w >> (bfs_bit & 31)) & 1u);
 		if (!rb) { bs = 0; be = 0; }
 		const uint32_t rB = rhi - rlo, sB = shi - slo;
 		const bool big = rB >= BLOCK_SIZE_THRESHOLD;       // src/qv.cc:843,962
@@ -262,12 +266,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			const uint64_t km = OSHFL(kmer, i);
 			const uint32_t k_rlo = OSHFL(rlo, i), k_rB = OSHFL(rB, i), k_slo = OSHFL(slo, i), k_sB = OSHFL(sB, i);
 			const uint32_t k_bs = OSHFL(bs, i), k_be = OSHFL(be, i);
-			const uint32_t k_fl = OSHFL((uint32_t)sb | ((uint32_t)big << 1), i);
+			const uint32_t k_qs = OSHFL(qs, i), k_qe = OSHFL(qe, i);
+			const bool k_big = OSHFL((uint32_t)big, i) != 0;
 			if (!on) continue;
-			const bool k_sb = k_fl & 1u, k_big = (k_fl >> 1) & 1u;
 			const uint32_t offset = 32u * i;
 			const uint32_t n0 = k_be - k_bs;                  // upper half, ref: LO32 bucket walk for the 48 queries of :1225
-			const uint32_t n1 = k_sb ? 36u : 0u;              // upper half, snp, d = 20..31 (:1305-1307)
+			const uint32_t n1 = k_qe - k_qs;                  // upper half, snp, d = 20..31 (:1305-1307): LO40 group walk for the 36 queries
 			const uint32_t n2 = k_big ? 12u : 0u;             // upper half, snp, d = 16..19 in big mode
 			const uint32_t n3 = k_big ? 48u : k_rB;           // lower half, ref: queries (:975) or strided scan (:358-373)
 			const uint32_t n4 = k_big ? 48u : k_sB;           // lower half, snp: queries (:977) or strided scan (:447-462)
@@ -281,10 +285,17 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					const uint2 en = ldr(reinterpret_cast<const uint2 *>(ix.ref_by_lo + k_bs + t));
 					const int sl = one_base_slot((uint64_t)(en.x ^ (uint32_t)(km >> 32)));
 					if (sl >= 0) { hit = true; nb = ((uint64_t)en.x << 32) | (uint32_t)km; v = en.y; d = 16u + (uint32_t)sl; }
-				} else if (t < e2 || (k_big && t >= e3)) {        // snp query
+				} else if (t < e1) {                              // LO40 group entry: same lower 20 bases, one base of the upper 12 differs?
+					const uint4 en = ldr(ix.snp_by_lo + k_qs + (t - e0));
+					const uint64_t ek = ((uint64_t)en.y << 32) | en.x;
+					const uint64_t x = ek ^ km;
+					if ((x & 0xFFFFFFFFFFull) == 0) {
+						const int sl = one_base_slot(x >> 40);
+						if (sl >= 0) { hit = true; list = 1; nb = ek; v = en.z; fi = en.w; d = 20u + (uint32_t)sl; }
+					}
+				} else if (t < e2 || (k_big && t >= e3)) {        // snp query (big mode only)
 					uint32_t u;
-					if (t < e1) { u = t - e0; d = 20u + u / 3; }
-					else if (t < e2) { u = t - e1; d = 16u + u / 3; }
+					if (t < e2) { u = t - e1; d = 16u + u / 3; }
 					else { u = t - e3; d = u / 3; }
 					nb = substitute(km, d, u % 3);
 					SnpEntry e;

@@ -225,6 +225,26 @@ __global__ void __launch_bounds__(256) k_scatter_by_lo(const RefEntry *ref, cons
 	}
 }
 
+// LO40-keyed view of the SNP dictionary (vgb_common.cuh): one thread per HI24 block walks its entries; cursor[] holds the
+// group starts on entry and the group ENDS on exit
+__global__ void __launch_bounds__(256) k_count_snp_lo(const SnpEntry *snp, uint64_t n, uint32_t *count)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) atomicAdd(&count[(uint32_t)((snp[i].key & 0xFFFFFFFFFFull) >> 10)], 1u);
+}
+__global__ void __launch_bounds__(256) k_scatter_snp_lo(const SnpEntry *snp, const uint32_t *jg24, uint32_t *cursor, uint4 *by_lo)
+{
+	const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;      // 2^24 blocks
+	const uint32_t lo = jg24[h], hi = jg24[h + 1];
+	for (uint32_t i = lo; i < hi; i++) {
+		const SnpEntry e = snp[i];
+		const uint64_t lo40 = e.key & 0xFFFFFFFFFFull;
+		const uint64_t kmer = (h << 40) | lo40;
+		const uint32_t slot = atomicAdd(&cursor[(uint32_t)(lo40 >> 10)], 1u);
+		by_lo[slot] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), e.pos, (uint32_t)(e.key >> 40) & 0xFFFFu);
+	}
+}
+
 __global__ void __launch_bounds__(256) k_max_u32(const uint32_t *a, uint64_t n, uint32_t *out)
 {
 	uint32_t m = 0;
@@ -497,6 +517,18 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	free_owned(c, d_sjg30);
 	ix.xdir = d_xdir;
+	{
+		// LO40-keyed view for the upper-half SNP neighbours: group sizes -> starts (in place) -> scatter (leaves the ends)
+		uint4 *d_sbl = nullptr; uint32_t *d_sdl = nullptr;
+		if ((rc = dev_alloc(c, &d_sbl, v->n_snp))) return rc;
+		if ((rc = dev_alloc(c, &d_sdl, (1ull << 30) + 1))) return rc;
+		VGB_CUDA(c, cudaMemsetAsync(d_sdl, 0, ((1ull << 30) + 1) * 4, c->stream));
+		if (v->n_snp) k_count_snp_lo<<<(unsigned)((v->n_snp + 255) / 256), 256, 0, c->stream>>>(d_snp, v->n_snp, d_sdl);
+		if ((rc = exclusive_scan_u32(c, d_sdl, d_sdl, 1ull << 30, d_tmp, nullptr))) return rc;
+		k_scatter_snp_lo<<<(unsigned)((1ull << 24) / 256), 256, 0, c->stream>>>(d_snp, d_sjg, d_sdl, d_sbl);
+		c->launches += 2;
+		ix.snp_by_lo = d_sbl; ix.snp_dir_lo = d_sdl;
+	}
 	{
 		// residue-major LO40 column for the strided scan
 		const uint64_t stride = (v->n_snp + SNP_STRIDE - 1) / SNP_STRIDE + 1;

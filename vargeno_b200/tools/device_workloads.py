@@ -44,6 +44,7 @@ class DeviceWorkload:
     setup_s: dict
     host_genome: Optional[np.ndarray] = None
     host_index: Optional[ib.Index] = None
+    host_haps: Optional[Tuple[np.ndarray, np.ndarray]] = None
 
 
 def repeat_ops(total: int, seed: int, frac: float) -> List[Tuple[int, int, int]]:
@@ -98,8 +99,10 @@ def _dict_side_ok(cat: np.ndarray, g: np.ndarray, chunk: int = 1 << 20) -> np.nd
 
 def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, seed: int, name: str, n_frac: float = 0.05,
           repeat_frac: float = 0.02, read_len: int = 150, keep_host: bool = False, verbose: bool = False,
-          blocks: Optional[List[Tuple[int, int]]] = None) -> DeviceWorkload:
-    """blocks: explicit (global start, length) N runs instead of the n_frac layout."""
+          blocks: Optional[List[Tuple[int, int]]] = None, motifs: Optional[List[Tuple[int, bytes]]] = None) -> DeviceWorkload:
+    """blocks: explicit (global start, length) N runs instead of the n_frac layout.
+    motifs: (global start, bytes) written over the random text after the repeat copies: a 16-base motif planted >= 100 times
+    gives a reference HI32 block of >= 100 entries, i.e. the reference's "big" neighbour mode (src/qv.cc:242-264,962)."""
     t = {}
     t0 = time.time()
     names = [n for n, _ in contigs]
@@ -111,6 +114,8 @@ def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, 
     ops = repeat_ops(total, seed, repeat_frac)
     for src, dst, ln in ops:
         g._ck(g.L.vgb_memcpy_d2d(g.h, gd + dst, gd + src, ln))
+    for pos, text in (motifs or []):
+        g.h2d(gd + int(pos), np.frombuffer(text, dtype=np.uint8))
     if blocks is None:
         blocks = n_blocks(starts, lens, n_frac)
     for s, l in blocks:
@@ -146,7 +151,7 @@ def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, 
     if verbose:
         print("device workload %s: %s %s" % (name, counts, {k: round(v, 2) for k, v in t.items()}), flush=True)
     return DeviceWorkload(name, names, starts, lens, total, h0d, h1d, read_len, seed, int(dict_ok.sum()), counts, t,
-                          cat if keep_host else None, host_index)
+                          cat if keep_host else None, host_index, (h0, h1) if keep_host else None)
 
 
 def build_s1(g: "geno.Genotyper", scale: float = 1.0, seed: int = 7, keep_host: bool = False, verbose: bool = False) -> DeviceWorkload:

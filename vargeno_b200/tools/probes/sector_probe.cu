@@ -54,6 +54,67 @@ __global__ void __launch_bounds__(256) k_probe(const uint4 *buf, uint64_t n_sect
 	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
+// sweep variant: MLP independent loads in flight per thread (the loop body above fixes 8), occupancy limited through dynamic
+// shared memory so that `ctas` CTAs of 256 threads are resident per SM
+template <int MODE, int MLP>
+__global__ void __launch_bounds__(256) k_probe_mlp(const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint64_t seed, unsigned long long *sink)
+{
+	extern __shared__ unsigned char occupancy_ballast[];
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t acc = 0;
+	uint64_t s = mix64(seed ^ (tid * 0x9E3779B97F4A7C15ull));
+	for (uint32_t i = 0; i < per_thread; i += MLP) {
+		uint4 v[MLP];
+#pragma unroll
+		for (int k = 0; k < MLP; k++) {
+			s = mix64(s + k + 1);
+			v[k] = load16<MODE>(buf + 2 * (s % n_sectors));
+		}
+#pragma unroll
+		for (int k = 0; k < MLP; k++) acc += v[k].x ^ v[k].w;
+	}
+	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+template <int MODE, int MLP>
+static void sweep_one(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink, int ctas)
+{
+	const size_t smem = ctas >= 8 ? 0 : (size_t)(220 * 1024 / ctas) & ~(size_t)1023;
+	cudaFuncSetAttribute(k_probe_mlp<MODE, MLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	int occ = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe_mlp<MODE, MLP>, 256, smem);
+	const unsigned grid = 148u * (unsigned)occ * 16u;
+	const uint32_t per_thread = 128;
+	const uint64_t loads = (uint64_t)grid * 256 * per_thread;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	k_probe_mlp<MODE, MLP><<<grid, 256, smem>>>(buf, n_sectors, per_thread, 1, sink);
+	cudaEventRecord(e0);
+	for (int r = 0; r < 3; r++) k_probe_mlp<MODE, MLP><<<grid, 256, smem>>>(buf, n_sectors, per_thread, 2 + r, sink);
+	cudaEventRecord(e1);
+	cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	ms /= 3;
+	printf("{\"sweep\": \"%s\", \"loads_in_flight_per_thread\": %d, \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"loads_in_flight_per_sm\": %d, \"ms\": %.3f, \"g_loads_per_s\": %.2f, \"err\": \"%s\"}\n",
+	       name, MLP, occ, occ * 8, occ * 256 * MLP, ms, loads / (ms * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+	fflush(stdout);
+}
+
+template <int MODE>
+static void sweep(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink)
+{
+	const int ctas[] = { 1, 2, 4, 8 };
+	for (int c : ctas) {
+		sweep_one<MODE, 1>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 2>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 4>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 8>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 16>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 32>(name, buf, n_sectors, sink, c);
+	}
+}
+
 static unsigned g_grid = 148 * 64;
 static uint32_t g_per_thread = 64;
 
@@ -101,6 +162,11 @@ int main(int argc, char **argv)
 	cudaMemset(buf, 1, bytes);
 	cudaMemset(sink, 0, 8);
 	const uint64_t n_sectors = bytes / 32;
+	if (argc > 3 && argv[3][0] == 's') {              // sweep: loads in flight per thread x CTAs per SM, for the two flavours that matter
+		sweep<4>("ld.global.nc.L2::64B 16B", buf, n_sectors, sink);
+		sweep<8>("ld.global.nc (__ldg) 4B", buf, n_sectors, sink);
+		return 0;
+	}
 	run<0>("ld.global.nc (__ldg) 16B", buf, n_sectors, sink);
 	if (argc > 3) {                                   // quick: only the two flavours that matter
 		run<4>("ld.global.nc.L2::64B 16B", buf, n_sectors, sink);
