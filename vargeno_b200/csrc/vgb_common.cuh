@@ -41,20 +41,37 @@ struct __align__(16) PileBlk {
 
 struct DevIndex {
 	const RefEntry *ref;        uint64_t n_ref;
-	// Combined directory, one 20-byte record (5 words) per value p of the top 30 bits of a k-mer, 2^30 + 1 records:
-	//   words 0..3  ref_jg[4p .. 4p+3]   ref_jg[h] = #reference entries with HI32 < h (the reference's jumpgate, src/qv.cc:539-584)
-	//   word  4     snp_jg30[p]          #SNP entries whose top 30 bits are < p: exact SNP queries land in a block of ~0-2 entries
-	//                                    (a GRCh38-sized SNP dictionary has ~23 entries per HI24 block = 4-5 dependent sectors per query)
-	// The end of a block is the next start (word k+1, or word 0 / word 4 of the next record).  Same 20 GiB as two separate
-	// arrays, but both directory pairs of a k-mer's exact queries sit within 40 consecutive bytes: one L2 request (128-byte
-	// line) instead of two in 2 of 3 cases.  k_geno8 runs at the L2 request rate of this part (profiles/r01_summary.md), so
-	// requests per read are what its time is made of.
-	const uint32_t *xdir;
+	// Combined directory: ONE 16-byte record per value p of the top 30 bits of a k-mer (2^30 records, 16 GiB), so that both
+	// directory answers of an exact query -- the HI32 block of the reference dictionary (the reference's jumpgate pair,
+	// src/qv.cc:219-233) and the top-30-bit block of the SNP dictionary -- arrive with one aligned load that cannot straddle a
+	// sector, together with fingerprints that spare the entry request of most queries whose k-mer is not in the block
+	// (half of all passes run on the wrong strand, where no k-mer is; at GRCh38 size 49 % of the HI32 blocks and 30 % of the
+	// SNP blocks are non-empty):
+	//   x  ref_base   ref_jg[4p]        (ref_jg[h] = #reference entries with HI32 < h)
+	//   y  snp_base   snp_jg30[p]       (#SNP entries whose top 30 bits are < p)
+	//   z  rc0 | rc1 << 8 | rc2 << 16 | rc3 << 24   with rc_k = ref_jg[4p + k + 1] - ref_jg[4p]  (each <= 254)
+	//   w  sc | sfp << 8 | rfp0 << 16 | rfp1 << 20 | rfp2 << 24 | rfp3 << 28
+	//        sc   = number of SNP entries in block p (<= 254)
+	//        sfp  = fp8 of the only entry when sc == 1;  rfp_k = fp4 of the only entry of HI32 block 4p + k when it has one entry
+	// Counts that do not fit (rare: low-complexity sequence) live in two short lists sorted by p, found by binary search:
+	// more than 254 reference entries under one 15-base prefix -> z == 0xFFFFFFFF, bounds in xovf_ref; more than 254 SNP
+	// entries in block p -> sc == 0xFF, bounds in xovf_snp.
+	const uint4 *xdir;
+	const uint32_t *xovf_ref;   uint32_t n_xovf_ref;   // records of 6 words: p, ref_jg[4p .. 4p+4]
+	const uint32_t *xovf_snp;   uint32_t n_xovf_snp;   // records of 3 words: p, snp_jg30[p], snp_jg30[p+1]
 	const uint32_t *ref_aux;    uint32_t n_ref_aux; uint32_t amb_lo;
 	// secondary view of the reference dictionary keyed by LO32: all entries that share the lower 16 bases sit in one
 	// bucket, so the 48 upper-half Hamming-1 neighbours of a k-mer (src/qv.cc:1213-1298) are answered by one bucket read
 	const RefEntry *ref_by_lo;  // {HI32(kmer), posx}, bucket order unspecified
-	const uint32_t *ref_jg_lo;  // 2^32 entries: END of the bucket of LO32 == l (start = end of bucket l-1, 0 for l == 0)
+	// Bucket bounds AND the reference Bloom gate of a low-quality k-mer in one 32-byte record (one sector, one request; they
+	// used to be a Bloom word + a pair of a 2^32-entry end array: two to three requests).  Both depend on LO32 only: the
+	// gate bit is the filter's answer for hash32(LO32) (src/generate_bf.h:112-131, src/qv.cc:955), precomputed per LO32 value.
+	// Record g covers the 12 values LO32 = 12 g .. 12 g + 11:
+	//   word 0      start of the bucket of LO32 = 12 g
+	//   words 1..6  c_0 .. c_11 as u16: end of bucket 12 g + j, relative to word 0
+	//   word 7      bits 0..11 the gates; bit 31: some c_j needs more than 16 bits -> bounds in lo12_ovf (sorted by g, rare)
+	const uint4 *lo12;
+	const uint32_t *lo12_ovf;   uint32_t n_lo12_ovf;   // records of 14 words: g, start, 12 absolute ends
 	const SnpEntry *snp;        uint64_t n_snp;
 	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678): the HI24 block the strided scan needs
 	// residue-major copy of the LO40 column for the strided scan (F13): step t of a scan that starts at rank lo examines rank
@@ -70,7 +87,6 @@ struct DevIndex {
 	//   snp_dir_lo[q] = END of the group q = LO40 >> 10 (start = end of group q - 1, 0 for q == 0); 2^30 entries
 	const uint4 *snp_by_lo;     const uint32_t *snp_dir_lo;
 	const uint32_t *snp_aux_pos; const uint8_t *snp_aux_info; uint32_t n_snp_aux;
-	const uint32_t *ref_bf;     uint64_t ref_bf_bits; uint64_t ref_bf_nw32;
 	const uint32_t *snp_bf;     uint64_t snp_bf_bits; uint64_t snp_bf_nw32;
 	const PileBlk  *pile;       uint64_t pile_len;   // positions [0, pile_len)
 	const uint8_t  *site_code;  // ref | alt << 2 per site
@@ -117,15 +133,6 @@ __device__ __forceinline__ uint64_t ldr(const uint64_t *p) { uint64_t v; asm("ld
 __device__ __forceinline__ uint2 ldr(const uint2 *p) { uint2 v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; }
 __device__ __forceinline__ uint4 ldr(const uint4 *p) { uint4 v; asm("ld.global.nc" VGB_RANDOM_LOAD_QUAL ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 
-// BloomFilter::check_value, value_range 32 (src/generate_bf.h:112-114)
-__device__ __forceinline__ bool bf_ref(const DevIndex &ix, uint32_t lo32)
-{
-	uint64_t bit = hash32(lo32);
-	if (ix.ref_bf_bits <= 0xFFFFFFFFull) bit %= ix.ref_bf_bits;   // 9.6e9 bits in practice: the modulo is the identity
-	const uint64_t w = bit >> 5;
-	if (w >= ix.ref_bf_nw32) return false;
-	return (ldr(ix.ref_bf + w) >> (bit & 31)) & 1u;
-}
 // value_range 40 (src/generate_bf.h:115-116)
 __device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
 {
@@ -135,21 +142,93 @@ __device__ __forceinline__ bool bf_snp(const DevIndex &ix, uint64_t lo40)
 	return (ldr(ix.snp_bf + w) >> (bit & 31)) & 1u;
 }
 
+__host__ __device__ __forceinline__ uint32_t fp4_ref(uint32_t lo32) { return (lo32 * 0x9E3779B1u) >> 28; }
+__host__ __device__ __forceinline__ uint32_t fp8_snp(uint64_t kmer) { return (uint32_t)(((kmer & 0x3FFFFFFFFull) * 0x9E3779B97F4A7C15ull) >> 56); }
+
+// overflow record of p (see DevIndex::xdir): list of `n` records of `stride` words sorted by their first word; returns word
+// 1 + idx of p's record (the rare path: kept out of line and free of local arrays, the callers are register-bound)
+static __device__ __forceinline__ uint32_t xovf_word(const uint32_t *tab, uint32_t n, uint32_t stride, uint32_t p, uint32_t idx)
+{
+	uint32_t lo = 0, hi = n;
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(tab + (uint64_t)stride * mid) <= p) lo = mid; else hi = mid; }
+	return __ldg(tab + (uint64_t)stride * lo + 1 + idx);
+}
+
+// Both directory answers of k-mer `kmer` from one 16-byte record: HI32 block [rlo, rhi) of the reference dictionary
+// (src/qv.cc:219-233, check_block_size :242-264) and top-30-bit block [flo, fhi) of the SNP dictionary.  rmay / smay: false
+// when the fingerprint proves that the k-mer is not the single entry of its block (the block bounds stay valid).
+__device__ __forceinline__ void dir_lookup(const DevIndex &ix, uint64_t kmer, uint32_t &rlo, uint32_t &rhi, uint32_t &flo, uint32_t &fhi,
+                                           bool &rmay, bool &smay)
+{
+	const uint32_t p = (uint32_t)(kmer >> 34), k = (uint32_t)(kmer >> 32) & 3u;
+	const uint4 r = ldr(ix.xdir + p);
+	rmay = true; smay = true;
+	if (r.z != 0xFFFFFFFFu) {
+		rlo = r.x + (((r.z << 8) >> (8 * k)) & 0xFFu);               // byte k of (z << 8) = rc_(k-1), byte 0 = 0
+		rhi = r.x + ((r.z >> (8 * k)) & 0xFFu);
+		if (rhi - rlo == 1u) rmay = ((r.w >> (16 + 4 * k)) & 15u) == fp4_ref((uint32_t)kmer);
+	} else {
+		rlo = xovf_word(ix.xovf_ref, ix.n_xovf_ref, 6, p, k);
+		rhi = xovf_word(ix.xovf_ref, ix.n_xovf_ref, 6, p, k + 1);
+	}
+	const uint32_t sc = r.w & 0xFFu;
+	if (sc != 0xFFu) {
+		flo = r.y;
+		fhi = r.y + sc;
+		if (sc == 1u) smay = ((r.w >> 8) & 0xFFu) == fp8_snp(kmer);
+	} else {
+		flo = xovf_word(ix.xovf_snp, ix.n_xovf_snp, 3, p, 0);
+		fhi = xovf_word(ix.xovf_snp, ix.n_xovf_snp, 3, p, 1);
+	}
+}
 // ref_jg[h] for h in [0, 2^32]
-__device__ __forceinline__ uint32_t ref_jg_at(const DevIndex &ix, uint64_t h) { return ldr(ix.xdir + (h >> 2) * 5 + (h & 3)); }
+__device__ __forceinline__ uint32_t ref_jg_at(const DevIndex &ix, uint64_t h)
+{
+	if (h >> 32) return (uint32_t)ix.n_ref;
+	const uint32_t p = (uint32_t)(h >> 2), k = (uint32_t)h & 3u;
+	const uint4 r = ldr(ix.xdir + p);
+	if (r.z == 0xFFFFFFFFu) return xovf_word(ix.xovf_ref, ix.n_xovf_ref, 6, p, k);
+	return r.x + (((r.z << 8) >> (8 * k)) & 0xFFu);
+}
 // jumpgate pair of the HI32 block (src/qv.cc:219-233, check_block_size :242-264)
 __device__ __forceinline__ void ref_block(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
 {
-	const uint64_t h = kmer >> 32;
-	const uint32_t k = (uint32_t)h & 3u;
-	const uint32_t *r = ix.xdir + (h >> 2) * 5 + k;
-	lo = ldr(r);
-	hi = ldr(r + 1 + (k == 3u));                     // word 4 of the record is the SNP directory: skip it
+	uint32_t flo, fhi; bool rm, sm;
+	dir_lookup(ix, kmer, lo, hi, flo, fhi, rm, sm);
+}
+// LO32 record (see DevIndex::lo12): Bloom gate of src/qv.cc:955 and the bounds of the bucket "same lower 16 bases"
+__device__ __forceinline__ void ref_lo_gate_bucket(const DevIndex &ix, uint32_t lo32, bool &gate, uint32_t &s, uint32_t &e)
+{
+	const uint32_t g = lo32 / 12u, j = lo32 - 12u * g;
+	const uint4 a = ldr(ix.lo12 + 2ull * g), b = ldr(ix.lo12 + 2ull * g + 1);
+	gate = (b.w >> j) & 1u;
+	if (b.w >> 31) {
+		s = j ? xovf_word(ix.lo12_ovf, ix.n_lo12_ovf, 14, g, j) : a.x;
+		e = xovf_word(ix.lo12_ovf, ix.n_lo12_ovf, 14, g, j + 1);
+		return;
+	}
+	// halfword h (0..11) of the six words a.y a.z a.w b.x b.y b.z
+	const uint32_t w[6] = { a.y, a.z, a.w, b.x, b.y, b.z };
+	uint32_t ce = 0, cs = 0;
+#pragma unroll
+	for (int h = 0; h < 12; h++) {
+		const uint32_t v = (w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
+		if ((uint32_t)h == j) ce = v;
+		if ((uint32_t)h + 1 == j) cs = v;
+	}
+	s = a.x + cs;
+	e = a.x + ce;
 }
 __device__ __forceinline__ void ref_lo_bucket(const DevIndex &ix, uint32_t lo32, uint32_t &s, uint32_t &e)
 {
-	e = ldr(ix.ref_jg_lo + lo32);
-	s = lo32 ? ldr(ix.ref_jg_lo + lo32 - 1) : 0u;
+	bool gate;
+	ref_lo_gate_bucket(ix, lo32, gate, s, e);
+}
+// BloomFilter::check_value, value_range 32 (src/generate_bf.h:112-114), through the precomputed gate bit
+__device__ __forceinline__ bool bf_ref(const DevIndex &ix, uint32_t lo32)
+{
+	const uint32_t g = lo32 / 12u, j = lo32 - 12u * g;
+	return (ldr(reinterpret_cast<const uint32_t *>(ix.lo12 + 2ull * g + 1) + 3) >> j) & 1u;
 }
 __device__ __forceinline__ void snp_lo_bucket(const DevIndex &ix, uint64_t lo40, uint32_t &s, uint32_t &e)
 {
@@ -180,9 +259,9 @@ __device__ __forceinline__ int64_t ref_find_in_block(const DevIndex &ix, uint32_
 }
 __device__ __forceinline__ int64_t ref_query(const DevIndex &ix, uint64_t kmer, uint32_t &posx)
 {
-	uint32_t lo, hi;
-	ref_block(ix, kmer, lo, hi);
-	if (lo >= hi) return -1;
+	uint32_t lo, hi, flo, fhi; bool rm, sm;
+	dir_lookup(ix, kmer, lo, hi, flo, fhi, rm, sm);
+	if (lo >= hi || !rm) return -1;
 	return ref_find_in_block(ix, (uint32_t)kmer, lo, hi, posx);
 }
 
@@ -207,19 +286,12 @@ __device__ __forceinline__ uint64_t snp_scan_lo40(const DevIndex &ix, uint32_t l
 {
 	return ldr(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
 }
-// block of the top 30 bits: only for exact membership (entry rank inside the HI24 block is not needed there)
-__device__ __forceinline__ void snp_block30(const DevIndex &ix, uint64_t kmer, uint32_t &lo, uint32_t &hi)
-{
-	const uint64_t h = kmer >> 34;
-	const uint32_t *r = ix.xdir + h * 5 + 4;
-	lo = ldr(r);
-	hi = ldr(r + 5);
-}
+// exact membership through the block of the top 30 bits (entry rank inside the HI24 block is not needed there)
 __device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
 {
-	uint32_t lo, hi;
-	snp_block30(ix, kmer, lo, hi);
-	if (lo >= hi) return -1;
+	uint32_t lo, hi, rlo, rhi; bool rm, sm;
+	dir_lookup(ix, kmer, rlo, rhi, lo, hi, rm, sm);
+	if (lo >= hi || !sm) return -1;
 	return snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, lo, hi, out);
 }
 

@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 					// that can answer one of those 48 queries sits in the LO32 bucket; one bucket walk replaces 48 probes
 					uint32_t bs = 0, be = 0;
 					if (rb) {
-						uint32_t v = 0;
-						if (lane < 2) v = (lane == 0) ? (((uint32_t)km) ? __ldg(ix.ref_jg_lo + (uint32_t)km - 1) : 0u) : __ldg(ix.ref_jg_lo + (uint32_t)km);
-						bs = __shfl_sync(0xffffffffu, v, 0);
-						be = __shfl_sync(0xffffffffu, v, 1);
+						uint32_t v0 = 0, v1 = 0;
+						if (lane == 0) ref_lo_bucket(ix, (uint32_t)km, v0, v1);
+						bs = __shfl_sync(0xffffffffu, v0, 0);
+						be = __shfl_sync(0xffffffffu, v1, 0);
 						if (lane == 0) st.nbrq += 48;             // the 48 reference queries this walk stands for
 					}
 					const uint32_t n0 = be - bs;

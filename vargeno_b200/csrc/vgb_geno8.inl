@@ -214,24 +214,19 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 		// ---- level 1: everything that depends only on the k-mer is put in flight together ----
 		const bool mine = run && ol < K;
-		uint32_t rlo = 0, rhi = 0, slo = 0, shi = 0, bfr_w = 0, bfs_w = 0, bs = 0, be = 0;
+		uint32_t rlo = 0, rhi = 0, slo = 0, shi = 0, bfs_w = 0, bs = 0, be = 0;
+		bool rb = false;
 		uint32_t f_lo = 0, f_hi = 0;                       // SNP block of the top 30 bits: exact membership only
-		uint64_t bfr_bit = 0, bfs_bit = 0;
+		uint64_t bfs_bit = 0;
 		const bool gates = mine && lowq;
-		if (mine) {
-			ref_block(ix, kmer, rlo, rhi);
-			snp_block30(ix, kmer, f_lo, f_hi);
-		}
+		bool rmay = false, smay = false;                   // false: the directory's fingerprint says "not the entry of this block"
+		if (mine) dir_lookup(ix, kmer, rlo, rhi, f_lo, f_hi, rmay, smay);
 		if (gates) {
 			snp_block(ix, kmer, slo, shi);                 // HI24 block: the strided scan walks it by rank (F13)
-			bfr_bit = hash32((uint32_t)kmer);
-			if (ix.ref_bf_bits <= 0xFFFFFFFFull) bfr_bit %= ix.ref_bf_bits;
 			bfs_bit = hash40(kmer & 0xFFFFFFFFFFull) % ix.snp_bf_bits;
-			if ((bfr_bit >> 5) < ix.ref_bf_nw32) bfr_w = ldr(ix.ref_bf + (bfr_bit >> 5));
 			if ((bfs_bit >> 5) < ix.snp_bf_nw32) bfs_w = ldr(ix.snp_bf + (bfs_bit >> 5));
-			ref_lo_bucket(ix, (uint32_t)kmer, bs, be);     // speculative: used only if the ref Bloom gate is open
+			ref_lo_gate_bucket(ix, (uint32_t)kmer, rb, bs, be);   // the reference Bloom gate and the LO32 bucket bounds: one record
 		}
-		const bool rb = gates && ((bfr_w >> (bfr_bit & 31)) & 1u);
 		const bool sb = gates && ((bfs_w >> (bfs_bit & 31)) & 1u);
 		// SNP gate open: bounds of the "same LO40" group that answers the 36 upper-half SNP queries (vgb_common.cuh); issued
 		// here so that it travels under the exact-entry searches
@@ -241,8 +236,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		if (mine) {
 			uint32_t posx = 0;
 			SnpEntry e;
-			if (rlo < rhi && ref_find_in_block(ix, (uint32_t)kmer, rlo, rhi, posx) >= 0) hit8(ix, os, 0, kmer, posx, 0, NO_MOD, 32u * ol, ol);
-			if (f_lo < f_hi && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, f_lo, f_hi, e) >= 0)
+			if (rlo < rhi && rmay && ref_find_in_block(ix, (uint32_t)kmer, rlo, rhi, posx) >= 0) hit8(ix, os, 0, kmer, posx, 0, NO_MOD, 32u * ol, ol);
+			if (f_lo < f_hi && smay && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, f_lo, f_hi, e) >= 0)
 				hit8(ix, os, 1, kmer, e.pos, (uint32_t)(e.key >> 40) & 0xFFFFu, NO_MOD, 32u * ol, ol);
 		}
 		if (!rb) { bs = 0; be = 0; }
@@ -274,7 +269,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			const uint32_t n1 = k_qe - k_qs;                  // upper half, snp, d = 20..31 (:1305-1307): LO40 group walk for the 36 queries
 			const uint32_t n2 = k_big ? 12u : 0u;             // upper half, snp, d = 16..19 in big mode
 			const uint32_t n3 = k_big ? 48u : k_rB;           // lower half, ref: queries (:975) or strided scan (:358-373)
-			const uint32_t n4 = k_big ? 48u : k_sB;           // lower half, snp: queries (:977) or strided scan (:447-462)
+			const uint32_t n4 = k_big ? 48u : 0u;             // lower half, snp: queries in big mode (:977); the strided scan runs below
 			const uint32_t e0 = n0, e1 = e0 + n1, e2 = e1 + n2, e3 = e2 + n3, e4 = e3 + n4;
 			for (uint32_t t = ol; t < e4; t += G) {
 				// every kind of task ends in "a dictionary entry was found" -> one shared tail (hit8)
@@ -293,7 +288,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 						const int sl = one_base_slot(x >> 40);
 						if (sl >= 0) { hit = true; list = 1; nb = ek; v = en.z; fi = en.w; d = 20u + (uint32_t)sl; }
 					}
-				} else if (t < e2 || (k_big && t >= e3)) {        // snp query (big mode only)
+				} else if (t < e2 || t >= e3) {                   // snp query (big mode only)
 					uint32_t u;
 					if (t < e2) { u = t - e1; d = 16u + u / 3; }
 					else { u = t - e3; d = u / 3; }
@@ -306,28 +301,54 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					nb = substitute(km, d, u % 3);
 					uint32_t posx;
 					if (ref_query(ix, nb, posx) >= 0) { hit = true; v = posx; }
-				} else if (t < e3) {                              // ref strided scan step (F13)
-					const uint32_t s = t - e2;
-					const uint64_t ex = (uint64_t)k_rlo + (uint64_t)REF_STRIDE * s;
+				} else {                                          // ref strided scan step (F13): t in [e2, e3)
+					const uint32_t st = t - e2;
+					const uint64_t ex = (uint64_t)k_rlo + (uint64_t)REF_STRIDE * st;
 					if (ex < ix.n_ref) {
 						const uint32_t entry_lo = ldr(&ix.ref[ex].lo);
 						const int dd = one_base_slot((uint64_t)((uint32_t)km ^ entry_lo));
-						if (dd >= 0) { hit = true; nb = (km & 0xFFFFFFFF00000000ull) | entry_lo; v = ldr(&ix.ref[k_rlo + s].posx); d = (uint32_t)dd; }
-					}
-				} else {                                          // snp strided scan step (F13).  Tried and not kept (profiles/r01_summary.md):
-				                                                  // four steps per task (+3 % / +9 % at GRCh38 size, -8 % on S1), prefetching the column (+4 % / -9 %)
-					const uint32_t s = t - e3;
-					const uint64_t ex = (uint64_t)k_slo + (uint64_t)SNP_STRIDE * s;
-					if (ex < ix.n_snp) {
-						const uint64_t entry_lo = snp_scan_lo40(ix, k_slo, s);
-						const int dd = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
-						if (dd >= 0) {
-							const uint4 raw = ldr(reinterpret_cast<const uint4 *>(ix.snp + k_slo + s));
-							hit = true; list = 1; nb = (km & 0xFFFFFF0000000000ull) | entry_lo; v = raw.z; fi = (raw.y >> 8) & 0xFFFFu; d = (uint32_t)dd;
-						}
+						if (dd >= 0) { hit = true; nb = (km & 0xFFFFFFFF00000000ull) | entry_lo; v = ldr(&ix.ref[k_rlo + st].posx); d = (uint32_t)dd; }
 					}
 				}
 				if (hit) hit8(ix, os, list, nb, v, fi, d, offset, i);
+			}
+			// SNP strided scan (F13, :447-462), small mode: step s examines LO40 of rank slo + 11 s = element cbase + s of the
+			// residue-major column.  16 bytes = two steps per load, two loads in flight per lane: a group covers 16 steps per trip
+			// (a GRCh38-sized block has ~23), and the trip holds nothing but loads and compares.  A step that matches is rare: it
+			// leaves the inner loop, records its hit contexts, and the scan resumes behind it.
+			if (!k_big && k_sB) {
+				// steps whose examined rank slo + 11 s lies past the end of the dictionary match nothing: cut them off
+				const uint32_t n_scan = min(k_sB, (uint32_t)((ix.n_snp - k_slo + (SNP_STRIDE - 1)) / SNP_STRIDE));
+				const uint64_t cbase = (uint64_t)(k_slo % SNP_STRIDE) * ix.snp_scan_stride + k_slo / SNP_STRIDE;
+				const uint32_t mis = (uint32_t)cbase & 1u;    // step 0 is the upper half of its 16-byte pair
+				const uint4 *colp = reinterpret_cast<const uint4 *>(ix.snp_scan + (cbase - mis));
+				const uint32_t npairs = (n_scan + mis + 1u) >> 1;
+				uint32_t sq = ol, sub = 0;                    // next pair of this lane, entry of the trip to resume at
+				while (sq < npairs) {
+					uint32_t found = 4, st_hit = 0, dd_hit = 0;
+					uint64_t lo_hit = 0;
+					do {
+						const uint4 A = ldr(colp + sq);
+						uint4 B = make_uint4(0, 0, 0, 0);
+						if (sq + G < npairs) B = ldr(colp + sq + G);
+#pragma unroll
+						for (uint32_t e = 0; e < 4; e++) {
+							const uint32_t st = 2u * (sq + (e >> 1) * G) + (e & 1u) - mis;   // scan step of this entry (below 0 wraps: fails the range test)
+							const uint4 w = e < 2 ? A : B;
+							const uint64_t entry_lo = (e & 1u) ? (((uint64_t)w.w << 32) | w.z) : (((uint64_t)w.y << 32) | w.x);
+							const int dd = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
+							if (found == 4 && e >= sub && dd >= 0 && st < n_scan) {
+								found = e; st_hit = st; dd_hit = (uint32_t)dd; lo_hit = entry_lo;
+							}
+						}
+						sub = found + 1;
+						if (sub >= 4) { sq += 2 * G; sub = 0; }
+					} while (found == 4 && sq < npairs);
+					if (found < 4) {
+						const uint4 raw = ldr(reinterpret_cast<const uint4 *>(ix.snp + k_slo + st_hit));   // REPORTED entry: rank slo + step (F13)
+						hit8(ix, os, 1, (km & 0xFFFFFF0000000000ull) | lo_hit, raw.z, (raw.y >> 8) & 0xFFFFu, dd_hit, offset, i);
+					}
+				}
 			}
 		}
 		__syncwarp();

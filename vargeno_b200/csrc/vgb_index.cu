@@ -245,6 +245,52 @@ __global__ void __launch_bounds__(256) k_scatter_snp_lo(const SnpEntry *snp, con
 	}
 }
 
+// LO32 records (vgb_common.cuh, DevIndex::lo12): ends[] = bucket ends of the LO32-keyed view, bf = the reference Bloom filter as the
+// file holds it (only its first 2^32 bits are addressable by hash32)
+constexpr uint64_t LO12_GROUPS = ((1ull << 32) + 11) / 12;
+constexpr uint32_t LO12_OVF_CAP = 1u << 20;
+__global__ void __launch_bounds__(256) k_lo12(const uint32_t *ends, const uint32_t *bf, uint64_t bf_bits, uint64_t bf_nw32, uint4 *out,
+                                               uint32_t *ovf, uint32_t *n_ovf)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= LO12_GROUPS) return;
+	const uint64_t l0 = 12 * g;
+	const uint32_t start = l0 ? ends[l0 - 1] : 0u;
+	uint32_t e[12], gates = 0, last = start;
+	for (int j = 0; j < 12; j++) {
+		const uint64_t l = l0 + j;
+		if (l >> 32) { e[j] = last; continue; }                       // past the last LO32 value: empty buckets
+		e[j] = last = ends[l];
+		uint64_t bit = hash32((uint32_t)l);
+		if (bf_bits <= 0xFFFFFFFFull) bit %= bf_bits;                 // 9.6e9 bits in practice: the modulo is the identity
+		const uint64_t w = bit >> 5;
+		if (w < bf_nw32 && ((bf[w] >> (bit & 31)) & 1u)) gates |= 1u << j;
+	}
+	uint32_t w[8] = { start, 0, 0, 0, 0, 0, 0, gates };
+	if (e[11] - start > 0xFFFFu) {
+		w[7] |= 0x80000000u;
+		const uint32_t slot = atomicAdd(n_ovf, 1u);
+		if (slot < LO12_OVF_CAP) { uint32_t *o = ovf + 14ull * slot; o[0] = (uint32_t)g; o[1] = start; for (int j = 0; j < 12; j++) o[2 + j] = e[j]; }
+	} else {
+		for (int j = 0; j < 12; j++) w[1 + (j >> 1)] |= (e[j] - start) << (16 * (j & 1));
+	}
+	out[2 * g] = make_uint4(w[0], w[1], w[2], w[3]);
+	out[2 * g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// sort a short device list of `n` records of `words` u32 by their first word (host side; the lists are rare-case tables)
+static int sort_records_by_first_word(vgb_ctx *c, uint32_t *d_list, uint32_t n, uint32_t words)
+{
+	if (n < 2) return VGB_OK;
+	std::vector<uint32_t> h((size_t)n * words), o(h.size()), order(n);
+	VGB_CUDA(c, copy_sync(c, h.data(), d_list, h.size() * 4, cudaMemcpyDeviceToHost));
+	for (uint32_t i = 0; i < n; i++) order[i] = i;
+	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h[(size_t)a * words] < h[(size_t)b * words]; });
+	for (uint32_t i = 0; i < n; i++) memcpy(&o[(size_t)i * words], &h[(size_t)order[i] * words], words * 4);
+	VGB_CUDA(c, copy_sync(c, d_list, o.data(), o.size() * 4, cudaMemcpyHostToDevice));
+	return VGB_OK;
+}
+
 __global__ void __launch_bounds__(256) k_max_u32(const uint32_t *a, uint64_t n, uint32_t *out)
 {
 	uint32_t m = 0;
@@ -290,24 +336,46 @@ __global__ void __launch_bounds__(256) k_parse_snp(const uint4 *raw, uint64_t fi
 	if (err) { atomicAdd(&po->errors, 1ull); atomicCAS(&po->first_error_kind, 0u, err); }
 }
 
-// combined directory (vgb_common.cuh): words 0..3 of record p = ref_jg[4p .. 4p+3]; record 2^30 holds the sentinel ref_jg[2^32]
-__global__ void __launch_bounds__(256) k_xdir_ref(const uint32_t *jg, uint32_t *x)
+// combined directory (vgb_common.cuh), reference half of record p: base, cumulative counts of the four HI32 blocks, their fp4
+constexpr uint32_t XOVF_CAP = 4u << 20;   // overflow records per list (low-complexity prefixes); beyond that the upload fails loudly
+__global__ void __launch_bounds__(256) k_xdir_ref(const uint32_t *jg, const RefEntry *ref, uint4 *x, uint32_t *ovf, uint32_t *n_ovf)
 {
 	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p > (1ull << 30)) return;
-	uint32_t *r = x + 5 * p;
-	if (p < (1ull << 30)) {
-		const uint4 a = *reinterpret_cast<const uint4 *>(jg + 4 * p);
-		r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+	if (p >= (1ull << 30)) return;
+	const uint4 a = *reinterpret_cast<const uint4 *>(jg + 4 * p);
+	const uint32_t j[5] = { a.x, a.y, a.z, a.w, jg[4 * p + 4] };
+	uint4 r = make_uint4(j[0], 0, 0, 0);
+	if (j[4] - j[0] > 254u) {
+		r.z = 0xFFFFFFFFu;
+		const uint32_t slot = atomicAdd(n_ovf, 1u);
+		if (slot < XOVF_CAP) { uint32_t *o = ovf + 6ull * slot; o[0] = (uint32_t)p; for (int k = 0; k < 5; k++) o[1 + k] = j[k]; }
 	} else {
-		r[0] = jg[4 * p]; r[1] = 0; r[2] = 0; r[3] = 0;
+		for (int k = 0; k < 4; k++) {
+			r.z |= (j[k + 1] - j[0]) << (8 * k);
+			if (j[k + 1] - j[k] == 1u) r.w |= fp4_ref(ref[j[k]].lo) << (16 + 4 * k);
+		}
 	}
+	x[p] = r;
 }
-// word 4 of record p = snp_jg30[p], p in [0, 2^30]
-__global__ void __launch_bounds__(256) k_xdir_snp(const uint32_t *sjg30, uint32_t *x)
+// SNP half of record p: base, count, fp8 of a single entry
+__global__ void __launch_bounds__(256) k_xdir_snp(const uint32_t *sjg30, const SnpEntry *snp, uint4 *x, uint32_t *ovf, uint32_t *n_ovf)
 {
 	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p <= (1ull << 30)) x[5 * p + 4] = sjg30[p];
+	if (p >= (1ull << 30)) return;
+	const uint32_t lo = sjg30[p], hi = sjg30[p + 1];
+	uint4 r = x[p];
+	r.y = lo;
+	if (hi - lo > 254u) {
+		r.w |= 0xFFu;
+		const uint32_t slot = atomicAdd(n_ovf, 1u);
+		if (slot < XOVF_CAP) { uint32_t *o = ovf + 3ull * slot; o[0] = (uint32_t)p; o[1] = lo; o[2] = hi; }
+	} else {
+		r.w |= hi - lo;
+		// the entry keeps LO40 of its k-mer; bits 34..39 are the low bits of p: the fingerprint covers the low 34 bits, which is
+		// what fp8_snp() takes from a full k-mer
+		if (hi - lo == 1u) r.w |= fp8_snp(snp[lo].key & 0xFFFFFFFFFFull) << 8;
+	}
+	x[p] = r;
 }
 
 __global__ void __launch_bounds__(256) k_snp_scan_layout(const SnpEntry *snp, uint64_t n, uint64_t stride, uint64_t *scan)
@@ -469,10 +537,33 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	// bucket sizes -> bucket starts (in place), then scatter; the cursor array ends up holding bucket ends
 	if ((rc = exclusive_scan_u32(c, d_jg_lo, d_jg_lo, 1ull << 32, d_tmp, nullptr))) return rc;
 	k_scatter_by_lo<<<(unsigned)((1ull << 32) / 256), 256, 0, c->stream>>>(d_ref, d_jg, d_jg_lo, d_by_lo);
+	{
+		// LO32 records: bucket bounds + reference Bloom gate per LO32 value; the 16 GiB end array and the filter are released
+		// ref filter: hash32() < 2^32 <= 9.6e9 bits, so only the first 2^26 words are addressable
+		uint64_t rw = v->ref_bf_nwords;
+		if (v->ref_bf_bits > 0xFFFFFFFFull) rw = std::min<uint64_t>(rw, 1ull << 26);
+		rw = std::min<uint64_t>(rw, (v->ref_bf_bits + 63) / 64);
+		uint32_t *d_rbf = nullptr, *d_lovf = nullptr, *d_nl = nullptr; uint4 *d_lo12 = nullptr;
+		if ((rc = dev_alloc(c, &d_rbf, rw * 2, false)) || (rc = dev_alloc(c, &d_lo12, 2 * LO12_GROUPS)) || (rc = dev_alloc(c, &d_lovf, 14ull * LO12_OVF_CAP)) ||
+		    (rc = dev_alloc(c, &d_nl, 1, false))) return rc;
+		if (rw) VGB_CUDA(c, cudaMemcpyAsync(d_rbf, v->ref_bf_words, rw * 8, cudaMemcpyDefault, c->stream));
+		VGB_CUDA(c, cudaMemsetAsync(d_nl, 0, 4, c->stream));
+		k_lo12<<<(unsigned)((LO12_GROUPS + 255) / 256), 256, 0, c->stream>>>(d_jg_lo, d_rbf, v->ref_bf_bits, rw * 2, d_lo12, d_lovf, d_nl);
+		c->launches++;
+		uint32_t nl = 0;
+		VGB_CUDA(c, copy_sync(c, &nl, d_nl, 4, cudaMemcpyDeviceToHost));
+		cudaFree(d_rbf); cudaFree(d_nl);
+		free_owned(c, d_jg_lo);
+		if (nl > LO12_OVF_CAP) return set_err(c, VGB_E_INDEX, "%u LO32 groups overflow their 16-bit counts (limit %u): sequence too repetitive for this layout", nl, LO12_OVF_CAP);
+		if ((rc = sort_records_by_first_word(c, d_lovf, nl, 14))) return rc;
+		ix.lo12 = d_lo12; ix.lo12_ovf = d_lovf; ix.n_lo12_ovf = nl;
+	}
 	// first half of the combined directory (vgb_common.cuh); the 16 GiB jumpgate itself is released before the SNP side allocates
-	uint32_t *d_xdir = nullptr;
-	if ((rc = dev_alloc(c, &d_xdir, ((1ull << 30) + 1) * 5))) return rc;
-	k_xdir_ref<<<(unsigned)(((1ull << 30) + 1 + 255) / 256), 256, 0, c->stream>>>(d_jg, d_xdir);
+	uint4 *d_xdir = nullptr; uint32_t *d_ovf_ref = nullptr, *d_ovf_snp = nullptr, *d_novf = nullptr;
+	if ((rc = dev_alloc(c, &d_xdir, 1ull << 30))) return rc;
+	if ((rc = dev_alloc(c, &d_ovf_ref, 6ull * XOVF_CAP)) || (rc = dev_alloc(c, &d_ovf_snp, 3ull * XOVF_CAP)) || (rc = dev_alloc(c, &d_novf, 2, false))) return rc;
+	VGB_CUDA(c, cudaMemsetAsync(d_novf, 0, 8, c->stream));
+	k_xdir_ref<<<(unsigned)((1ull << 30) / 256), 256, 0, c->stream>>>(d_jg, d_ref, d_xdir, d_ovf_ref, d_novf);
 	c->launches += 2;
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	free_owned(c, d_jg);
@@ -481,7 +572,7 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	if (po.errors) return set_err(c, VGB_E_INDEX, "reference dictionary: %llu bad records (%s)", po.errors, parse_err_text(po.first_error_kind));
 	if (po.max_pos >= amb_lo) return set_err(c, VGB_E_INDEX, "reference dictionary: %s", parse_err_text(2));
 	ix.ref = d_ref; ix.n_ref = v->n_ref; ix.ref_aux = d_aux; ix.n_ref_aux = (uint32_t)v->n_ref_aux; ix.amb_lo = amb_lo;
-	ix.ref_by_lo = d_by_lo; ix.ref_jg_lo = d_jg_lo;
+	ix.ref_by_lo = d_by_lo;
 
 	// ---- SNP dictionary + static pileup ----
 	// SNP k-mer starts are reference k-mer starts, so sites lie below max_pos + 32 (src/qv.cc:596-603)
@@ -512,11 +603,22 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	if ((rc = fill_jumpgate(c, d_sjg, 24, (uint32_t)v->n_snp, d_tmp))) return rc;
 	if ((rc = fill_jumpgate(c, d_sjg30, 30, (uint32_t)v->n_snp, d_tmp))) return rc;
 	// second half of the combined directory; the separate array is not needed any more
-	k_xdir_snp<<<(unsigned)(((1ull << 30) + 1 + 255) / 256), 256, 0, c->stream>>>(d_sjg30, d_xdir);
+	k_xdir_snp<<<(unsigned)((1ull << 30) / 256), 256, 0, c->stream>>>(d_sjg30, d_snp, d_xdir, d_ovf_snp, d_novf + 1);
 	c->launches++;
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	free_owned(c, d_sjg30);
 	ix.xdir = d_xdir;
+	{
+		// the two overflow lists were appended in no particular order: sort them by p on the host (they are short)
+		uint32_t novf[2];
+		VGB_CUDA(c, copy_sync(c, novf, d_novf, 8, cudaMemcpyDeviceToHost));
+		cudaFree(d_novf);
+		if (novf[0] > XOVF_CAP || novf[1] > XOVF_CAP)
+			return set_err(c, VGB_E_INDEX, "%u / %u directory records overflow their 8-bit counts (limit %u): sequence too repetitive for this layout", novf[0], novf[1], XOVF_CAP);
+		if ((rc = sort_records_by_first_word(c, d_ovf_ref, novf[0], 6)) || (rc = sort_records_by_first_word(c, d_ovf_snp, novf[1], 3))) return rc;
+		ix.xovf_ref = d_ovf_ref; ix.n_xovf_ref = novf[0];
+		ix.xovf_snp = d_ovf_snp; ix.n_xovf_snp = novf[1];
+	}
 	{
 		// LO40-keyed view for the upper-half SNP neighbours: group sizes -> starts (in place) -> scatter (leaves the ends)
 		uint4 *d_sbl = nullptr; uint32_t *d_sdl = nullptr;
@@ -571,18 +673,11 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 	VGB_CUDA(c, cudaMemsetAsync(d_cnt, 0, 2ull * n_sites * 4, c->stream));
 	ix.pile = d_pile; ix.pile_len = pile_len; ix.site_code = d_code; ix.n_sites = n_sites; ix.cnt = d_cnt;
 
-	// ---- Bloom filters ----
-	// ref: hash32() < 2^32 <= 9.6e9 bits, so only the first 2^26 words are addressable
-	uint64_t rw = v->ref_bf_nwords;
-	if (v->ref_bf_bits > 0xFFFFFFFFull) rw = std::min<uint64_t>(rw, 1ull << 26);
-	rw = std::min<uint64_t>(rw, (v->ref_bf_bits + 63) / 64);
+	// ---- SNP Bloom filter (the reference one lives on as the gate bits of the LO32 records) ----
 	const uint64_t sw = std::min<uint64_t>(v->snp_bf_nwords, (v->snp_bf_bits + 63) / 64);
-	uint32_t *d_rbf, *d_sbf;
-	if ((rc = dev_alloc(c, &d_rbf, rw * 2))) return rc;
+	uint32_t *d_sbf;
 	if ((rc = dev_alloc(c, &d_sbf, sw * 2))) return rc;
-	if (rw) VGB_CUDA(c, cudaMemcpyAsync(d_rbf, v->ref_bf_words, rw * 8, cudaMemcpyDefault, c->stream));
 	if (sw) VGB_CUDA(c, cudaMemcpyAsync(d_sbf, v->snp_bf_words, sw * 8, cudaMemcpyDefault, c->stream));
-	ix.ref_bf = d_rbf; ix.ref_bf_bits = v->ref_bf_bits; ix.ref_bf_nw32 = rw * 2;
 	ix.snp_bf = d_sbf; ix.snp_bf_bits = v->snp_bf_bits; ix.snp_bf_nw32 = sw * 2;
 
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
