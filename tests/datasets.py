@@ -170,4 +170,25 @@ def make_adv_b(d: str) -> Dataset:
     return _write(d, "advB", g, snps, parts, sample_columns=True, declare_gt=True)
 
 
-MAKERS = {"s0": make_s0, "advA": make_adv_a, "advB": make_adv_b}
+def make_big100(d: str) -> Dataset:
+    """105 Mbp in two contigs with 400 repeat families (2..14 copies of 300..3300 bases, 0..2 mutations per copy: thousands of
+    aux rows and POS_AMBIGUOUS entries whose column ORDER depends on how the reference's qsort treats equal k-mers), a planted
+    16-base motif (big HI32 block) and 300 k SNPs: the size at which the index builder's byte-identity is pinned
+    (tests/golden/big100.json holds the sha256 of the files the compiled reference wrote).  No reads."""
+    fams = []
+    for f in range(400):
+        r = int(synth.rnd64(101, 50, f))
+        fams.append((300 + r % 3000, 2 + (r >> 20) % 13, (r >> 30) % 3, f + 1))
+    g = synth.make_genome([("chr1", 60_000_000), ("chr2", 45_000_000)], seed=101,
+                          n_runs=[(0, 0, 10000), (0, 30_000_000, 1_500_000), (1, 20_000_000, 50_000), (1, 44_990_000, 10_000)],
+                          repeats=fams, motifs=[(b"TTGACCGATAGGCATC", 150)])
+    snps = synth.make_snps(g, 300_000, seed=101, cluster_frac=0.1)
+    os.makedirs(d, exist_ok=True)
+    fa, vcf, fq = (os.path.join(d, x) for x in ("ref.fa", "snp.vcf", "reads.fq"))
+    synth.write_fasta(g, fa)
+    synth.write_vcf(g, snps, vcf)
+    open(fq, "wb").close()
+    return Dataset("big100", d, fa, vcf, fq, 0)
+
+
+MAKERS = {"s0": make_s0, "advA": make_adv_a, "advB": make_adv_b, "big100": make_big100}

@@ -61,8 +61,9 @@ def _sha(path):
 
 @pytest.mark.parametrize("name", ["s0", "advA", "advB"])
 def test_cli_index_files_are_byte_identical(cache, name, tmp_path):
-    """`vargeno-b200 index` (text parsing on the host, sort / collapse / Bloom filters on the GPU) must write the five files the
-    compiled reference's `vargeno index` wrote: sizes and sha256 from tests/golden/<name>.json."""
+    """`vargeno-b200 index` (text parsing on the host, sort / collapse / Bloom filters on the GPU) must write the files the
+    compiled reference's `vargeno index` wrote -- the five `geno` reads and the .ref.bf.lite.bf nothing reads
+    (src/generate_bf.cc:102-105,145-163): sizes and sha256 from tests/golden/<name>.json."""
     import json
     vb.build()
     man = json.load(open(os.path.join(GOLD, name + ".json")))
@@ -70,7 +71,30 @@ def test_cli_index_files_are_byte_identical(cache, name, tmp_path):
     prefix = str(tmp_path / "cli")
     p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix, "--verbose"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 0, p.stderr
-    for ext in ("ref.dict", "snp.dict", "ref.bf", "snp.bf", "chrlens"):
+    for ext in ("ref.dict", "snp.dict", "ref.bf", "snp.bf", "chrlens", "ref.bf.lite.bf"):
+        assert os.path.getsize(prefix + "." + ext) == man["index_bytes"][ext], ext
+        assert _sha(prefix + "." + ext) == man["index"][ext], ext
+    if name == "s0":            # --no-lite leaves the sixth file out and changes nothing else
+        p2 = str(tmp_path / "nolite")
+        p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, p2, "--no-lite"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr
+        assert not os.path.exists(p2 + ".ref.bf.lite.bf") and _sha(p2 + ".ref.dict") == man["index"]["ref.dict"]
+
+
+def test_cli_index_at_100_mbp_with_repeat_families(cache, tmp_path):
+    """SURVEY 8(f)-1 at a size where the reference's `qsort` order of EQUAL k-mers shows (aux-row column order): 105 Mbp, 400
+    repeat families, 686 589 aux rows.  tests/golden/big100.json holds the sha256 of what the compiled reference's `vargeno
+    index` wrote for exactly this FASTA + VCF (inputs are pinned by their own sha256; the reference run is reproducible with
+    VG_RUN_REF=1 pytest tests/test_oracle_golden.py -k big100)."""
+    import json
+    vb.build()
+    man = json.load(open(os.path.join(GOLD, "big100.json")))
+    ds = cache.dataset("big100")
+    assert _sha(ds.fasta) == man["inputs"]["ref.fa"] and _sha(ds.vcf) == man["inputs"]["snp.vcf"]
+    prefix = str(tmp_path / "big")
+    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix, "--verbose"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    for ext in ("chrlens", "snp.bf", "snp.dict", "ref.dict", "ref.bf", "ref.bf.lite.bf"):
         assert os.path.getsize(prefix + "." + ext) == man["index_bytes"][ext], ext
         assert _sha(prefix + "." + ext) == man["index"][ext], ext
 
@@ -80,7 +104,7 @@ def test_cli_index_then_geno(cache, tmp_path):
     vb.build()
     ds = cache.dataset("s0")
     prefix = str(tmp_path / "ix")
-    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.vcf, prefix, "--no-lite"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 0, p.stderr
     out = str(tmp_path / "out.vcf")
     p = subprocess.run([vb.HOST_BIN, "geno", prefix, ds.fastq, ds.vcf, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)

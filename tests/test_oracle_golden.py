@@ -109,3 +109,23 @@ def test_rerun_compiled_reference(cache, name, tmp_path):
     o = orc.Oracle(cache.index(name))
     o.process_fastq(np.fromfile(ds.fastq, dtype=np.uint8), trace_path=str(tmp_path / "t_mine"))
     assert open(str(tmp_path / "t_ref"), "rb").read() == open(str(tmp_path / "t_mine"), "rb").read()
+
+
+@pytest.mark.ref
+def test_rerun_reference_index_big100(cache, tmp_path):
+    """Opt-in (VG_RUN_REF=1, ~2 min, ~6 GB): the compiled reference's `vargeno index` on the 105 Mbp repeat-family set writes the
+    files whose sha256 tests/golden/big100.json holds (what `vargeno-b200 index` is compared with on the GPU box)."""
+    import hashlib
+    import json
+    import subprocess
+    assert orc.have_ref()
+    man = json.load(open(os.path.join(GOLD, "big100.json")))
+    ds = cache.dataset("big100")
+    prefix = str(tmp_path / "ref")
+    subprocess.check_call([orc.REF_BIN, "index", ds.fasta, ds.vcf, prefix], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for ext, want in man["index"].items():
+        h = hashlib.sha256()
+        with open(prefix + "." + ext, "rb") as f:
+            for blk in iter(lambda: f.read(1 << 24), b""):
+                h.update(blk)
+        assert h.hexdigest() == want, ext

@@ -66,6 +66,6 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 // the whole `index` command: FASTA + VCF text -> device builder -> the five index files (index_host.cpp)
 // dump_parse: write the parsed contigs / SNP lines as text to that file and stop before the device step (host-logic tests)
 int run_index(const std::string &fasta, const std::string &vcf, const std::string &prefix, int device, bool verbose,
-              const std::string &dump_parse = std::string());
+              const std::string &dump_parse = std::string(), bool write_lite = true);
 
 }  // namespace vgh

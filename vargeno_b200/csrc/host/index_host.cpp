@@ -3,7 +3,8 @@
 // the GPU (vgb_build_index_device, csrc/vgb_build.cu).  The host keeps what is text: the two FASTA readers, the two VCF
 // walks with their filters, and the file formats.  The five files `geno` reads come out byte-identical to the
 // reference's (tests/test_gpu_cli.py compares them with the sha256 of reference-built files in tests/golden/).
-// Not written: <prefix>.ref.bf.lite.bf (2.3 GB, written by the reference, read by nothing: src/generate_bf.cc:161-170).
+// <prefix>.ref.bf.lite.bf (2.3 GB, written by the reference, read by nothing: src/generate_bf.cc:102-105,145-163) is written
+// too unless --no-lite is given.
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -254,7 +255,8 @@ bool write_bitvector(vgb_ctx *ctx, const std::string &path, const uint64_t *dwor
 
 }  // namespace
 
-int run_index(const std::string &fasta, const std::string &vcf_path, const std::string &prefix, int device, bool verbose, const std::string &dump_parse)
+int run_index(const std::string &fasta, const std::string &vcf_path, const std::string &prefix, int device, bool verbose, const std::string &dump_parse,
+              bool write_lite)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	auto secs = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
@@ -316,6 +318,16 @@ int run_index(const std::string &fasta, const std::string &vcf_path, const std::
 		}
 		if (!write_bitvector(ctx, prefix + ".ref.bf", view.ref_bf_words, view.ref_bf_bits, view.ref_bf_nwords, buf, err)) break;
 		if (!write_bitvector(ctx, prefix + ".snp.bf", view.snp_bf_words, view.snp_bf_bits, view.snp_bf_nwords, buf, err)) break;
+		if (write_lite) {   // the sixth file of the reference's `index`
+			uint64_t *d_lite = nullptr, bits = 0, nw = 0;
+			if (vgb_build_ref_lite_bf_device(ctx, (const uint8_t *)d_genome, fa.starts.data(), fa.lens.data(), (uint32_t)fa.names.size(), &d_lite, &bits, &nw) != VGB_OK) {
+				err = vgb_last_error(ctx);
+				break;
+			}
+			const bool ok = write_bitvector(ctx, prefix + ".ref.bf.lite.bf", d_lite, bits, nw, buf, err);
+			vgb_device_free(ctx, d_lite);
+			if (!ok) break;
+		}
 		{   // .chrlens (src/qv.cc:2344-2346)
 			FILE *f = fopen((prefix + ".chrlens").c_str(), "w");
 			if (!f) { err = "cannot create " + prefix + ".chrlens"; break; }

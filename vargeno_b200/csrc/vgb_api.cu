@@ -310,6 +310,7 @@ int vgb_reset_counts(vgb_ctx *c)
 	for (int s = 0; s < 2; s++) VGB_CUDA(c, vgb::memset_sync(c, c->chunk[s].d_meta, 0, 64));
 	c->trace_n = 0; c->sticky_format = 0;
 	c->chunks = c->chunk_bytes = 0; c->ms_parse = c->ms_geno = 0; c->launches = 0;
+	if (c->have_index && getenv("VGB_RETUNE")) return geno_prepare(c);   // tuning runs: re-read the VGB_* kernel knobs without a new index upload
 	return VGB_OK;
 }
 
@@ -422,6 +423,14 @@ int vgb_build_index_device(vgb_ctx *c, const uint8_t *device_genome, uint64_t ge
 	cudaSetDevice(c->device);
 	return build_index_device(c, device_genome, genome_len, cstart, clen, n_contigs, snp_pos0, snp_code, snp_rf, snp_af, n_snp_lines,
 	                          bf_pos0, n_bf_lines, out);
+}
+
+int vgb_build_ref_lite_bf_device(vgb_ctx *c, const uint8_t *device_genome, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs,
+                                 uint64_t **device_words, uint64_t *bits, uint64_t *nwords)
+{
+	if (!c || !device_genome || !cstart || !clen || !device_words || !bits || !nwords) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return build_ref_lite_bf(c, device_genome, cstart, clen, n_contigs, device_words, bits, nwords);
 }
 
 void vgb_free_index_device(vgb_ctx *c, vgb_index_view *view)

@@ -66,15 +66,50 @@ __global__ void __launch_bounds__(256) k_make_probe_kmers(const DevIndex ix, uin
 	kmers[i] = (lo << 32) | ix.ref[idx].lo;
 }
 
+// Persistent grid, U k-mers per thread and trip, the probes of a trip issued level by level: U directory records, then the
+// first entry of every block that can hold the k-mer (its fingerprint matches), then -- only for longer blocks -- the search.
+// (One k-mer per thread and one tiny CTA per 256 k-mers spent more time launching CTAs than probing: 17 G fetches/s.)
+constexpr int PROBE_U = 4;
 __global__ void __launch_bounds__(256) k_probe(const DevIndex ix, const uint64_t *kmers, uint64_t n, unsigned long long *found)
 {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
 	uint32_t f = 0;
-	if (i < n) {
-		const uint64_t km = kmers[i];
-		uint32_t posx;
-		SnpEntry e;
-		f = (ref_query(ix, km, posx) >= 0) + (snp_query(ix, km, e) >= 0);
+	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += T * PROBE_U) {
+		uint64_t km[PROBE_U];
+		uint4 r[PROBE_U];
+		bool on[PROBE_U];
+#pragma unroll
+		for (int j = 0; j < PROBE_U; j++) { on[j] = base + j * T < n; km[j] = on[j] ? __ldg(kmers + base + j * T) : 0; }
+#pragma unroll
+		for (int j = 0; j < PROBE_U; j++) r[j] = ldr(ix.xdir + (uint32_t)(km[j] >> 34));
+		uint32_t rlo[PROBE_U], rhi[PROBE_U], flo[PROBE_U], fhi[PROBE_U];
+		bool rq[PROBE_U], sq[PROBE_U];
+		uint2 re[PROBE_U];
+		uint4 se[PROBE_U];
+#pragma unroll
+		for (int j = 0; j < PROBE_U; j++) {
+			bool rm, sm;
+			dir_decode(ix, r[j], km[j], rlo[j], rhi[j], flo[j], fhi[j], rm, sm);
+			rq[j] = on[j] && rm && rlo[j] < rhi[j];
+			sq[j] = on[j] && sm && flo[j] < fhi[j];
+			re[j] = make_uint2(0, 0); se[j] = make_uint4(0, 0, 0, 0);
+			if (rq[j]) re[j] = ldr(reinterpret_cast<const uint2 *>(ix.ref + rlo[j]));
+			if (sq[j]) se[j] = ldr(reinterpret_cast<const uint4 *>(ix.snp + flo[j]));
+		}
+#pragma unroll
+		for (int j = 0; j < PROBE_U; j++) {
+			if (rq[j]) {
+				uint32_t posx;
+				if (re[j].x == (uint32_t)km[j]) f++;
+				else if (rhi[j] - rlo[j] > 1 && ref_find_in_block(ix, (uint32_t)km[j], rlo[j] + 1, rhi[j], posx) >= 0) f++;
+			}
+			if (sq[j]) {
+				SnpEntry e;
+				const uint64_t key = (((uint64_t)se[j].y << 32) | se[j].x) & 0xFFFFFFFFFFull;
+				if (key == (km[j] & 0xFFFFFFFFFFull)) f++;
+				else if (fhi[j] - flo[j] > 1 && snp_find_in_block(ix, km[j] & 0xFFFFFFFFFFull, flo[j] + 1, fhi[j], e) >= 0) f++;
+			}
+		}
 	}
 	f = __reduce_add_sync(0xffffffffu, f);
 	if ((threadIdx.x & 31) == 0 && f) atomicAdd(found, (unsigned long long)f);
@@ -87,8 +122,11 @@ int probe_bench(vgb_ctx *c, uint64_t n, int mode, uint64_t seed, int repeats, do
 	int rc;
 	if ((rc = dev_alloc(c, &d_k, n, false))) return rc;
 	if ((rc = dev_alloc(c, &d_f, 1, false))) { cudaFree(d_k); return rc; }
-	const unsigned grid = (unsigned)((n + 255) / 256);
-	k_make_probe_kmers<<<grid, 256, 0, c->stream>>>(c->ix, d_k, n, mode, seed);
+	const unsigned mk_grid = (unsigned)((n + 255) / 256);
+	int occ = 1;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, 256, 0);
+	const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * (occ > 0 ? occ : 1), (n + 255) / 256);
+	k_make_probe_kmers<<<mk_grid, 256, 0, c->stream>>>(c->ix, d_k, n, mode, seed);
 	cudaMemsetAsync(d_f, 0, 8, c->stream);
 	k_probe<<<grid, 256, 0, c->stream>>>(c->ix, d_k, n, d_f);       // warm-up
 	cudaMemsetAsync(d_f, 0, 8, c->stream);

@@ -20,6 +20,7 @@ namespace vgb {
 
 constexpr uint64_t REF_BF_BITS = 1200000000ull * 8;   // src/generate_bf.h:201
 constexpr uint64_t SNP_BF_BITS = 140000000ull * 8;    // src/generate_bf.h:203
+constexpr uint64_t REF_LITE_BF_BITS = 2300000000ull * 8;   // src/generate_bf.h:202
 
 __device__ __forceinline__ uint32_t base2(uint8_t c)   // A0 C1 G2 T3, anything else 4 (fasta_parser.c maps it to 'N')
 {
@@ -148,6 +149,52 @@ __global__ void __launch_bounds__(256) k_write_snp(const uint64_t *keys, const u
 			st32u(col, p); col[4] = info; col[5] = rf; col[6] = af;
 		}
 	} else { st32u(r + 8, POS_AMBIGUOUS); r[12] = 0; r[13] = 1; r[14] = 0; r[15] = 0; }
+}
+
+// <prefix>.ref.bf.lite.bf (src/generate_bf.cc:102-105,145-163): LO40 of every N-free 32-mer of every contig, value_range 40.
+// Written by the reference's `index`, read by nothing; produced here so that `index` leaves the same set of files behind.
+// Thread t owns the 32 k-mer starts cs + 32 t .. cs + 32 t + 31 (same walk as k_build_kmers).
+__global__ void __launch_bounds__(256) k_bf_lite(const uint8_t *g, uint64_t cs, uint64_t ce, uint32_t *words32)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t s0 = cs + t * 32;
+	if (s0 + 32 > ce) return;
+	uint64_t km = 0, nmask = 0;
+	for (int j = 0; j < 63; j++) {
+		const uint64_t p = s0 + j;
+		const uint32_t c = p < ce ? base2(g[p]) : 4u;
+		if (j < 32) km |= (uint64_t)(c & 3) << (2 * j);
+		if (c == 4) nmask |= 1ull << j;
+	}
+	for (int j = 0; j < 32; j++) {
+		const uint64_t s = s0 + j;
+		if (s + 32 > ce) break;
+		if (j > 0) km = (km >> 2) | ((uint64_t)(base2(g[s + 31]) & 3) << 62);
+		if (((nmask >> j) & 0xFFFFFFFFull) == 0) {
+			const uint64_t bit = hash40(km & 0xFFFFFFFFFFull) % REF_LITE_BF_BITS;
+			atomicOr(&words32[bit >> 5], 1u << (bit & 31));
+		}
+	}
+}
+
+int build_ref_lite_bf(vgb_ctx *c, const uint8_t *d_genome, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs,
+                      uint64_t **d_words, uint64_t *bits, uint64_t *nwords)
+{
+	const uint64_t nw = (REF_LITE_BF_BITS + 63) / 64;
+	uint32_t *w = nullptr;
+	int rc;
+	if ((rc = dev_alloc(c, &w, nw * 2, false))) return rc;
+	VGB_CUDA(c, cudaMemsetAsync(w, 0, nw * 8, c->stream));
+	for (uint32_t k = 0; k < n_contigs; k++) {
+		if (clen[k] < 32) continue;
+		const uint64_t threads = (clen[k] - 31 + 31) / 32;
+		k_bf_lite<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_genome, cstart[k], cstart[k] + clen[k], w);
+		c->launches++;
+	}
+	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
+	VGB_CUDA(c, cudaGetLastError());
+	*d_words = reinterpret_cast<uint64_t *>(w); *bits = REF_LITE_BF_BITS; *nwords = nw;
+	return VGB_OK;
 }
 
 // reference Bloom filter: LO32 of every dictionary k-mer (src/generate_bf.cc:146-147); hash32 % 9.6e9 is the identity

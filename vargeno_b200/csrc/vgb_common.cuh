@@ -157,11 +157,10 @@ static __device__ __forceinline__ uint32_t xovf_word(const uint32_t *tab, uint32
 // Both directory answers of k-mer `kmer` from one 16-byte record: HI32 block [rlo, rhi) of the reference dictionary
 // (src/qv.cc:219-233, check_block_size :242-264) and top-30-bit block [flo, fhi) of the SNP dictionary.  rmay / smay: false
 // when the fingerprint proves that the k-mer is not the single entry of its block (the block bounds stay valid).
-__device__ __forceinline__ void dir_lookup(const DevIndex &ix, uint64_t kmer, uint32_t &rlo, uint32_t &rhi, uint32_t &flo, uint32_t &fhi,
+__device__ __forceinline__ void dir_decode(const DevIndex &ix, const uint4 r, uint64_t kmer, uint32_t &rlo, uint32_t &rhi, uint32_t &flo, uint32_t &fhi,
                                            bool &rmay, bool &smay)
 {
 	const uint32_t p = (uint32_t)(kmer >> 34), k = (uint32_t)(kmer >> 32) & 3u;
-	const uint4 r = ldr(ix.xdir + p);
 	rmay = true; smay = true;
 	if (r.z != 0xFFFFFFFFu) {
 		rlo = r.x + (((r.z << 8) >> (8 * k)) & 0xFFu);               // byte k of (z << 8) = rc_(k-1), byte 0 = 0
@@ -180,6 +179,11 @@ __device__ __forceinline__ void dir_lookup(const DevIndex &ix, uint64_t kmer, ui
 		flo = xovf_word(ix.xovf_snp, ix.n_xovf_snp, 3, p, 0);
 		fhi = xovf_word(ix.xovf_snp, ix.n_xovf_snp, 3, p, 1);
 	}
+}
+__device__ __forceinline__ void dir_lookup(const DevIndex &ix, uint64_t kmer, uint32_t &rlo, uint32_t &rhi, uint32_t &flo, uint32_t &fhi,
+                                           bool &rmay, bool &smay)
+{
+	dir_decode(ix, ldr(ix.xdir + (uint32_t)(kmer >> 34)), kmer, rlo, rhi, flo, fhi, rmay, smay);
 }
 // ref_jg[h] for h in [0, 2^32]
 __device__ __forceinline__ uint32_t ref_jg_at(const DevIndex &ix, uint64_t h)

@@ -532,7 +532,11 @@ int geno_prepare(vgb_ctx *c)
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
 	for (int gi = 0; gi < 2 && !warp_only; gi++) {
 		const size_t sm = grp_smem_bytes(gi ? 8 : 4);   // hit contexts + one row of counters per warp + the warp's parked reads
-		for (int t = 0; t < 2; t++) VGB_CUDA(c, cudaFuncSetAttribute(grp[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		for (int t = 0; t < 2; t++) {
+			VGB_CUDA(c, cudaFuncSetAttribute(grp[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+			// VGB_CARVEOUT: preferred shared-memory share of the unified L1 / shared array in percent (tuning knob; default: the driver's choice)
+			if (const char *e = getenv("VGB_CARVEOUT")) VGB_CUDA(c, cudaFuncSetAttribute(grp[gi][t], cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+		}
 		VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, grp[gi][0], GW * 32, sm));
 		if (occ < 1) occ = 1;
 		c->grp_grid[gi] = (uint32_t)(c->sm_count * occ);

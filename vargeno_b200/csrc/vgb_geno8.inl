@@ -18,7 +18,10 @@
 // k-mers + quality gates) and the warp runs a retry round as soon as a full set is waiting -- so the second pass, which
 // half of all reads need (reverse-strand reads), is executed with every group busy instead of half of them.
 
-constexpr int OCT_EV = 24;            // hit contexts per read kept in shared memory (16 measured the same on S1 and at GRCh38 size)
+#ifndef VGB_OCT_EV
+#define VGB_OCT_EV 24
+#endif
+constexpr int OCT_EV = VGB_OCT_EV;    // hit contexts per read kept in shared memory (16 measured the same on S1 and at GRCh38 size)
 
 // per-round counters of one read, in the group's shared memory (committed when the round ends, unless the read is
 // deferred in this round); the first eight A_* slots of the per-warp accumulator have the same meaning

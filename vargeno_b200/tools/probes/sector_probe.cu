@@ -54,64 +54,73 @@ __global__ void __launch_bounds__(256) k_probe(const uint4 *buf, uint64_t n_sect
 	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
-// sweep variant: MLP independent loads in flight per thread (the loop body above fixes 8), occupancy limited through dynamic
-// shared memory so that `ctas` CTAs of 256 threads are resident per SM
+// sweep variant: MLP independent DEPENDENT-ADDRESS chains per thread (the next address of a chain is computed from the loaded
+// value, so exactly MLP loads per thread are in flight, whatever the compiler does), `ctas` CTAs of 256 threads per SM, and
+// `ballast` bytes of dynamic shared memory per CTA (what a kernel's own shared memory takes away from the unified L1)
 template <int MODE, int MLP>
 __global__ void __launch_bounds__(256) k_probe_mlp(const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint64_t seed, unsigned long long *sink)
 {
 	extern __shared__ unsigned char occupancy_ballast[];
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t acc = 0;
-	uint64_t s = mix64(seed ^ (tid * 0x9E3779B97F4A7C15ull));
+	uint64_t s[MLP];
+#pragma unroll
+	for (int k = 0; k < MLP; k++) s[k] = mix64(seed ^ ((tid * MLP + k) * 0x9E3779B97F4A7C15ull));
 	for (uint32_t i = 0; i < per_thread; i += MLP) {
 		uint4 v[MLP];
 #pragma unroll
-		for (int k = 0; k < MLP; k++) {
-			s = mix64(s + k + 1);
-			v[k] = load16<MODE>(buf + 2 * (s % n_sectors));
-		}
+		for (int k = 0; k < MLP; k++) v[k] = load16<MODE>(buf + 2 * (s[k] % n_sectors));
 #pragma unroll
-		for (int k = 0; k < MLP; k++) acc += v[k].x ^ v[k].w;
+		for (int k = 0; k < MLP; k++) s[k] = mix64(s[k] + v[k].x + 1);
 	}
+	uint64_t acc = 0;
+#pragma unroll
+	for (int k = 0; k < MLP; k++) acc ^= s[k];
 	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
 template <int MODE, int MLP>
-static void sweep_one(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink, int ctas)
+static void sweep_one(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink, int ctas, size_t ballast)
 {
-	const size_t smem = ctas >= 8 ? 0 : (size_t)(220 * 1024 / ctas) & ~(size_t)1023;
-	cudaFuncSetAttribute(k_probe_mlp<MODE, MLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaFuncSetAttribute(k_probe_mlp<MODE, MLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ballast);
 	int occ = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe_mlp<MODE, MLP>, 256, smem);
-	const unsigned grid = 148u * (unsigned)occ * 16u;
-	const uint32_t per_thread = 128;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe_mlp<MODE, MLP>, 256, ballast);
+	if (occ > ctas) occ = ctas;
+	const unsigned grid = 148u * (unsigned)occ;                      // one wave: exactly `occ` CTAs per SM
+	const uint32_t per_thread = 2048;
 	const uint64_t loads = (uint64_t)grid * 256 * per_thread;
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	k_probe_mlp<MODE, MLP><<<grid, 256, smem>>>(buf, n_sectors, per_thread, 1, sink);
+	k_probe_mlp<MODE, MLP><<<grid, 256, ballast>>>(buf, n_sectors, per_thread, 1, sink);
 	cudaEventRecord(e0);
-	for (int r = 0; r < 3; r++) k_probe_mlp<MODE, MLP><<<grid, 256, smem>>>(buf, n_sectors, per_thread, 2 + r, sink);
+	for (int r = 0; r < 2; r++) k_probe_mlp<MODE, MLP><<<grid, 256, ballast>>>(buf, n_sectors, per_thread, 2 + r, sink);
 	cudaEventRecord(e1);
 	cudaEventSynchronize(e1);
 	float ms = 0;
 	cudaEventElapsedTime(&ms, e0, e1);
-	ms /= 3;
-	printf("{\"sweep\": \"%s\", \"loads_in_flight_per_thread\": %d, \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"loads_in_flight_per_sm\": %d, \"ms\": %.3f, \"g_loads_per_s\": %.2f, \"err\": \"%s\"}\n",
-	       name, MLP, occ, occ * 8, occ * 256 * MLP, ms, loads / (ms * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+	ms /= 2;
+	printf("{\"sweep\": \"%s\", \"loads_in_flight_per_thread\": %d, \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"loads_in_flight_per_sm\": %d, \"smem_per_sm_kb\": %.0f, \"ms\": %.3f, \"g_loads_per_s\": %.2f, \"err\": \"%s\"}\n",
+	       name, MLP, occ, occ * 8, occ * 256 * MLP, occ * (ballast + 1024) / 1024.0, ms, loads / (ms * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
 	fflush(stdout);
 }
 
 template <int MODE>
 static void sweep(const char *name, const uint4 *buf, uint64_t n_sectors, unsigned long long *sink)
 {
+	// (1) loads in flight per thread x resident CTAs per SM, no shared memory
 	const int ctas[] = { 1, 2, 4, 8 };
 	for (int c : ctas) {
-		sweep_one<MODE, 1>(name, buf, n_sectors, sink, c);
-		sweep_one<MODE, 2>(name, buf, n_sectors, sink, c);
-		sweep_one<MODE, 4>(name, buf, n_sectors, sink, c);
-		sweep_one<MODE, 8>(name, buf, n_sectors, sink, c);
-		sweep_one<MODE, 16>(name, buf, n_sectors, sink, c);
-		sweep_one<MODE, 32>(name, buf, n_sectors, sink, c);
+		sweep_one<MODE, 1>(name, buf, n_sectors, sink, c, 0);
+		sweep_one<MODE, 2>(name, buf, n_sectors, sink, c, 0);
+		sweep_one<MODE, 4>(name, buf, n_sectors, sink, c, 0);
+		sweep_one<MODE, 8>(name, buf, n_sectors, sink, c, 0);
+		sweep_one<MODE, 16>(name, buf, n_sectors, sink, c, 0);
+	}
+	// (2) the shape of k_geno8 (4 CTAs of 256 threads per SM) with more and more shared memory per CTA
+	const size_t ballast[] = { 0, 7 << 10, 15 << 10, 24 << 10, 32 << 10, 40 << 10, 48 << 10, 56 << 10 };
+	for (size_t b : ballast) {
+		sweep_one<MODE, 2>(name, buf, n_sectors, sink, 4, b);
+		sweep_one<MODE, 4>(name, buf, n_sectors, sink, 4, b);
+		sweep_one<MODE, 8>(name, buf, n_sectors, sink, 4, b);
 	}
 }
 
