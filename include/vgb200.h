@@ -179,6 +179,10 @@ int  vgb_build_index_device(vgb_ctx *ctx, const uint8_t *device_genome, uint64_t
                             const uint32_t *snp_pos0, const uint8_t *snp_code, const uint8_t *snp_ref_freq, const uint8_t *snp_alt_freq,
                             uint64_t n_snp_lines, const uint32_t *bf_pos0, uint64_t n_bf_lines, vgb_index_view *out);
 void vgb_free_index_device(vgb_ctx *ctx, vgb_index_view *view);
+/* SNP Bloom filter for the UCSC snp-table input (constructBfFromUcsc, src/generate_bf.cc:439-592): 33 values per accepted record
+ * (positions 0-based in the concatenation, alternative allele as a 2-bit code); words in device memory, release with vgb_device_free */
+int  vgb_build_snp_bf_ucsc_device(vgb_ctx *ctx, const uint8_t *device_genome, const uint32_t *pos0, const uint8_t *alt_code, uint64_t n_lines,
+                                  uint64_t **device_words, uint64_t *bits, uint64_t *nwords);
 /* <prefix>.ref.bf.lite.bf, the sixth file `vargeno index` writes (src/generate_bf.cc:102-105,145-163; read by nothing): LO40 of
  * every N-free 32-mer, as sdsl bit_vector words in device memory; release with vgb_device_free */
 int  vgb_build_ref_lite_bf_device(vgb_ctx *ctx, const uint8_t *device_genome, const uint64_t *contig_starts, const uint64_t *contig_lens,

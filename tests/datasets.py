@@ -25,6 +25,7 @@ class Dataset:
     vcf: str
     fastq: str
     n_reads: int
+    txt: str = ""      # UCSC snp-table dump of the same SNP list (legacy input format), when the set has one
 
 
 def _snpset_from_rows(rows) -> synth.SnpSet:
@@ -170,6 +171,28 @@ def make_adv_b(d: str) -> Dataset:
     return _write(d, "advB", g, snps, parts, sample_columns=True, declare_gt=True)
 
 
+def make_ucsc_a(d: str) -> Dataset:
+    """The advA genome with its SNP list as a UCSC snp141Common-style table (src/dictgen.c:350-540,
+    src/generate_bf.cc:439-592): both strands, shuffled allele order, records of every kind the filters drop."""
+    fams = []
+    for f in range(40):
+        r = int(synth.rnd64(11, 50, f))
+        fams.append((100 + r % 500, 1 + (r >> 20) % 12, (r >> 30) % 3, f + 1))
+    g = synth.make_genome([("chr1", 260000), ("chr2", 180000)], seed=11,
+                          n_runs=[(0, 50000, 250), (0, 200000, 31), (1, 90000, 1000), (1, 100, 5)], repeats=fams)
+    rows = _rows(synth.make_snps(g, 1500, seed=12, cluster_frac=0.3))
+    _snps_in_repeats(g, 12, [f[3] for f in fams if f[2] == 0][:8], 2, rows)
+    snps = _snpset_from_rows(rows)
+    os.makedirs(d, exist_ok=True)
+    fa, vcf, fq, txt = (os.path.join(d, x) for x in ("ref.fa", "snp.vcf", "reads.fq", "snp.txt"))
+    synth.write_fasta(g, fa)
+    synth.write_vcf(g, snps, vcf)
+    synth.write_ucsc_txt(g, snps, txt, seed=12)
+    haps = synth.donor_haplotypes(g, snps, seed=12)
+    synth.simulate_reads(g, haps, 6000, 150, seed=12, sub_rate=0.01, lowq_prob=0.4).tofile(fq)
+    return Dataset("ucscA", d, fa, vcf, fq, 6000, txt)
+
+
 def make_big100(d: str) -> Dataset:
     """105 Mbp in two contigs with 400 repeat families (2..14 copies of 300..3300 bases, 0..2 mutations per copy: thousands of
     aux rows and POS_AMBIGUOUS entries whose column ORDER depends on how the reference's qsort treats equal k-mers), a planted
@@ -191,4 +214,4 @@ def make_big100(d: str) -> Dataset:
     return Dataset("big100", d, fa, vcf, fq, 0)
 
 
-MAKERS = {"s0": make_s0, "advA": make_adv_a, "advB": make_adv_b, "big100": make_big100}
+MAKERS = {"s0": make_s0, "advA": make_adv_a, "advB": make_adv_b, "big100": make_big100, "ucscA": make_ucsc_a}

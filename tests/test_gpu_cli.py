@@ -99,6 +99,25 @@ def test_cli_index_at_100_mbp_with_repeat_families(cache, tmp_path):
         assert _sha(prefix + "." + ext) == man["index"][ext], ext
 
 
+def test_cli_index_from_ucsc_table_then_geno(cache, tmp_path):
+    """`vargeno-b200 index ref.fa snps.txt prefix` (UCSC snp-table input) writes the files the compiled reference's
+    `ucscd` + `ucscbf` wrote, and `geno` on that index gives the reference's VCF (tests/golden/ucscA.*)."""
+    import json
+    vb.build()
+    man = json.load(open(os.path.join(GOLD, "ucscA.json")))
+    ds = cache.dataset("ucscA")
+    prefix = str(tmp_path / "u")
+    p = subprocess.run([vb.HOST_BIN, "index", ds.fasta, ds.txt, prefix], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    for ext in ("ref.dict", "snp.dict", "ref.bf", "snp.bf", "chrlens", "ref.bf.lite.bf"):
+        assert os.path.getsize(prefix + "." + ext) == man["index_bytes"][ext], ext
+        assert _sha(prefix + "." + ext) == man["index"][ext], ext
+    out = str(tmp_path / "out.vcf")
+    p = subprocess.run([vb.HOST_BIN, "geno", prefix, ds.fastq, ds.vcf, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "ucscA.out.vcf"), "rb").read()
+
+
 def test_cli_index_then_geno(cache, tmp_path):
     """The two commands back to back, as a user of the reference would run them."""
     vb.build()

@@ -66,6 +66,8 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 // the whole `index` command: FASTA + VCF text -> device builder -> the five index files (index_host.cpp)
 // dump_parse: write the parsed contigs / SNP lines as text to that file and stop before the device step (host-logic tests)
 int run_index(const std::string &fasta, const std::string &vcf, const std::string &prefix, int device, bool verbose,
-              const std::string &dump_parse = std::string(), bool write_lite = true);
+              const std::string &dump_parse = std::string(), bool write_lite = true, const std::string &snp_locs_path = std::string());
+// `filt`: dict_filt of the reference (src/dict_filt.c:23-79), host only
+int run_filt(const std::string &ref_dict, const std::string &snp_locs, const std::string &out_path);
 
 }  // namespace vgh

@@ -216,6 +216,152 @@ bool vcf_for_bf(const MappedFile &vcf, const Fasta &fa, SnpLines &out, std::stri
 	return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// UCSC snp-table input: the legacy SNP format of the reference (`vargeno ucscd` / `ucscbf`, src/qv.cc:1954-2008,
+// 2225-2238; the same code sits commented out in its `index`, :2246-2314).  Columns: 1 chrom, 2 chromStart (0-based), 6 strand,
+// 7 refNCBI, 8 refUCSC, 9 observed, 11 class, 21 alleleFreqCount, 22 alleles, 24 alleleFreqs.
+// ---------------------------------------------------------------------------------------------------------------
+struct UcscBfLines { std::vector<uint32_t> pos0; std::vector<uint8_t> alt; };   // lines that reach the insert loop of constructBfFromUcsc
+
+inline uint8_t rev_base(uint8_t c)       // rev(), src/dictgen.c:322-345: complement of an upper- or lower-case base, anything else unchanged
+{
+	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; default: return c; }
+}
+inline bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// dictionary side: make_snp_dict, src/dictgen.c:350-540.  snp_locs (optional): the bool-per-position table the reference
+// keeps for `filt` (index = 1-based position in the concatenation; src/dictgen.c:459-466, written only #if GEN_FLT_DATA).
+bool ucsc_for_dict(const MappedFile &txt, const Fasta &fa, SnpLines &out, std::vector<uint8_t> *snp_locs, std::string &err)
+{
+	if (snp_locs) snp_locs->assign(10, 0);
+	long ci = -1;                                       // `chrom` of the reference's loop: survives records of unknown contigs
+	const char *p = (const char *)txt.data, *end = p + txt.size;
+	uint64_t lineno = 0;
+	while (p < end) {
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+		const char *le = nl ? nl : end;
+		const char *b = p;
+		p = nl ? nl + 1 : end;
+		lineno++;
+		if (b == le || *b == '#') continue;
+		if ((uint64_t)(le - b) >= 5999) { err = "UCSC table line " + std::to_string(lineno) + " is longer than the reference's 6000-byte buffer (src/dictgen.c:362)"; return false; }
+		const std::vector<std::string> f = split_tabs(b, le);
+		if (f.size() < 25) { err = "UCSC table line " + std::to_string(lineno) + " has fewer than 25 columns (undefined in the reference)"; return false; }
+		std::string chrom;
+		for (char ch : f[1]) { if (c_isspace((uint8_t)ch) || chrom.size() >= 49) break; chrom.push_back(ch); }
+		if (f[7].empty() || f[8].empty()) continue;
+		const uint8_t ref_b = up((uint8_t)f[7][0]);
+		const uint8_t rc = CODE.c[ref_b];
+		if (rc == BASE_X || strncmp(f[11].c_str(), "single", 6) != 0 || ref_b != up((uint8_t)f[8][0])) continue;
+		if (f[7].size() != 1 || f[8].size() != 1) continue;                           // reference alleles one base long (:417)
+		if (ci < 0 || fa.names[ci] != chrom) {
+			ci = -1;
+			for (size_t k = 0; k < fa.names.size(); k++) if (fa.names[k] == chrom) { ci = (long)k; break; }
+			if (ci < 0) continue;
+		}
+		const uint64_t index = (uint32_t)atoi(f[2].c_str());
+		const uint8_t *seq = fa.norm.data() + fa.starts[ci];
+		const uint64_t len = fa.lens[ci];
+		if (index >= len || up(seq[index]) != ref_b) {
+			err = "Mismatch found between reference sequence and SNP file at 0-based index " + std::to_string(index) + " in " + fa.names[ci] +
+			      " (the reference exits, src/dictgen.c:431-437)";
+			return false;
+		}
+		if (index < 32 || index + 32 > len) continue;
+		if (f[21].empty() || f[21][0] != '2') continue;                               // bi-allelic only (:444)
+		const bool neg = !f[6].empty() && f[6][0] == '-';
+		if (!neg && (f[6].empty() || f[6][0] != '+')) { err = "strand is neither + nor - at line " + std::to_string(lineno) + " (the reference asserts, src/dictgen.c:450)"; return false; }
+		if (f[22].size() < 3) { err = "alleles column too short at line " + std::to_string(lineno); return false; }
+		const uint8_t a1 = neg ? rev_base(up((uint8_t)f[22][0])) : up((uint8_t)f[22][0]);
+		const uint8_t a2 = neg ? rev_base(up((uint8_t)f[22][2])) : up((uint8_t)f[22][2]);
+		if (!is_acgt(a1) || !is_acgt(a2)) { err = "allele outside ACGT at line " + std::to_string(lineno) + " (the reference asserts, src/dictgen.c:455-456)"; return false; }
+		if (a1 != ref_b && a2 != ref_b) continue;
+		if (snp_locs) {
+			const uint64_t loc = fa.starts[ci] + 1 + index;
+			if (loc >= snp_locs->size()) snp_locs->resize(loc + 1, 0);
+			(*snp_locs)[loc] = 1;
+		}
+		const char *fq = f[24].c_str();
+		double f1 = (float)atof(fq);
+		const char *comma = strchr(fq, ',');
+		if (!comma) { err = "alleleFreqs without a comma at line " + std::to_string(lineno) + " (the reference runs off the buffer, src/dictgen.c:470)"; return false; }
+		double f2 = (float)atof(comma + 1);
+		if (a2 == ref_b) std::swap(f1, f2);
+		for (char chv : f[9]) {                                                       // observed: the first usable alternative allele decides (:481-517)
+			if (c_isspace((uint8_t)chv)) break;
+			const uint8_t alt = neg ? rev_base(up((uint8_t)chv)) : up((uint8_t)chv);
+			if (alt == ref_b || !is_acgt(alt)) continue;
+			bool skip = false;
+			for (uint64_t k = index - 32; k < index; k++) if (CODE.c[seq[k]] == BASE_N) { skip = true; break; }
+			for (uint64_t k = index + 1; k < index + 32 && !skip; k++) if (seq[k] == 'N' || seq[k] == 'n') skip = true;
+			if (!skip) {
+				out.pos0.push_back((uint32_t)(fa.starts[ci] + index));
+				out.code.push_back((uint8_t)(rc | (CODE.c[alt] << 2)));
+				out.rf.push_back(freq_enc(f1));
+				out.af.push_back(freq_enc(f2));
+			}
+			break;
+		}
+	}
+	return true;
+}
+
+// Bloom-filter side: constructBfFromUcsc, src/generate_bf.cc:439-592 (raw FASTA view: whole header line as the name; the stale
+// sequence is kept when a contig is unknown; "single" must match exactly here, a prefix is enough on the dictionary side)
+bool ucsc_for_bf(const MappedFile &txt, const Fasta &fa, UcscBfLines &out, std::string &err)
+{
+	std::string pre = "XO";
+	long ci = -1;
+	const uint8_t *seq = nullptr;
+	uint64_t len = 0;
+	const char *p = (const char *)txt.data, *end = p + txt.size;
+	uint64_t lineno = 0;
+	while (p < end) {
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+		const char *le = nl ? nl : end;
+		const char *b = p;
+		p = nl ? nl + 1 : end;
+		lineno++;
+		if (b == le || *b == '#') continue;
+		const std::vector<std::string> c = split_tabs(b, le);
+		if (c.size() < 25) { err = "UCSC table line " + std::to_string(lineno) + " has fewer than 25 columns (undefined in the reference)"; return false; }
+		if (c[7].empty() || c[8].empty()) continue;
+		const uint8_t ref_b = up((uint8_t)c[7][0]);
+		if (CODE.c[ref_b] == BASE_X || c[11] != "single" || ref_b != up((uint8_t)c[8][0])) continue;
+		if (c[7].size() != 1 || c[8].size() != 1) continue;
+		if (c[1] != pre) {
+			bool found = false;
+			for (size_t k = 0; k < fa.raw_names.size(); k++)
+				if (fa.raw_names[k] == c[1]) { seq = fa.raw.data() + fa.starts[k]; len = fa.lens[k]; ci = (long)k; found = true; break; }
+			if (!found) continue;
+			pre = c[1];
+		}
+		const uint64_t index = (uint64_t)(uint32_t)strtol(c[2].c_str(), nullptr, 10);
+		if (index >= len || up(seq[index]) != ref_b) { err = "Mismatch found between reference sequence and SNP file at 0-based index " + std::to_string(index) + " (the reference exits, src/generate_bf.cc:507-510)"; return false; }
+		if (index < 32 || index + 32 > len) continue;
+		if (c[21] != "2") continue;
+		const bool neg = !c[6].empty() && c[6][0] == '-';
+		if (!neg && (c[6].empty() || c[6][0] != '+')) { err = "strand is neither + nor - at line " + std::to_string(lineno); return false; }
+		if (c[22].size() < 3) { err = "alleles column too short at line " + std::to_string(lineno); return false; }
+		const uint8_t a1 = neg ? rev_base(up((uint8_t)c[22][0])) : up((uint8_t)c[22][0]);
+		const uint8_t a2 = neg ? rev_base(up((uint8_t)c[22][2])) : up((uint8_t)c[22][2]);
+		if (!is_acgt(a1) || !is_acgt(a2)) { err = "allele outside ACGT at line " + std::to_string(lineno); return false; }
+		if (a1 != ref_b && a2 != ref_b) continue;
+		bool any = false;
+		for (char chv : c[9]) {
+			if (c_isspace((uint8_t)chv)) break;
+			const uint8_t alt = neg ? rev_base(up((uint8_t)chv)) : up((uint8_t)chv);
+			if (alt == ref_b || !is_acgt(alt)) continue;
+			out.pos0.push_back((uint32_t)(fa.starts[ci] + index));
+			out.alt.push_back(CODE.c[alt]);
+			any = true;
+			break;
+		}
+		if (!any) { err = "observed column without a usable alternative allele at line " + std::to_string(lineno) + " (the reference runs off the string, src/generate_bf.cc:536)"; return false; }
+	}
+	return true;
+}
+
 bool write_all(int fd, const void *buf, uint64_t n)
 {
 	const uint8_t *p = (const uint8_t *)buf;
@@ -255,9 +401,12 @@ bool write_bitvector(vgb_ctx *ctx, const std::string &path, const uint64_t *dwor
 
 }  // namespace
 
+static bool ends_with(const std::string &s, const char *suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+
 int run_index(const std::string &fasta, const std::string &vcf_path, const std::string &prefix, int device, bool verbose, const std::string &dump_parse,
-              bool write_lite)
+              bool write_lite, const std::string &snp_locs_path)
 {
+	const bool ucsc = ends_with(vcf_path, ".txt");      // the reference tells its two SNP formats apart by extension (src/qv.cc:2244-2246,2315)
 	const auto t0 = std::chrono::steady_clock::now();
 	auto secs = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
 	std::string err;
@@ -266,9 +415,22 @@ int run_index(const std::string &fasta, const std::string &vcf_path, const std::
 	MappedFile vcf;
 	if (!vcf.open(vcf_path, err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
 	SnpLines sl;
-	if (!vcf_for_dict(vcf, fa, sl, err) || !vcf_for_bf(vcf, fa, sl, err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	UcscBfLines ub;
+	std::vector<uint8_t> snp_locs;
+	const bool ok_parse = ucsc ? (ucsc_for_dict(vcf, fa, sl, snp_locs_path.empty() ? nullptr : &snp_locs, err) && ucsc_for_bf(vcf, fa, ub, err))
+	                           : (vcf_for_dict(vcf, fa, sl, err) && vcf_for_bf(vcf, fa, sl, err));
+	if (!ok_parse) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	if (!snp_locs_path.empty() && !ucsc) { fprintf(stderr, "vargeno-b200: --snp-locs goes with the UCSC table input (src/qv.cc:1988-1996)\n"); return EXIT_FAILURE; }
 	if (verbose) fprintf(stderr, "parsed %zu contigs, %zu bp, %zu dictionary SNP lines, %zu Bloom-filter SNP lines (%.2f s)\n", fa.names.size(),
-	                     fa.norm.size(), sl.pos0.size(), sl.bf_pos0.size(), secs());
+	                     fa.norm.size(), sl.pos0.size(), ucsc ? ub.pos0.size() : sl.bf_pos0.size(), secs());
+	if (!snp_locs_path.empty()) {
+		// the table `filt` takes: u64 size, then one byte per 1-based concatenated position (src/qv.cc:1988-1996)
+		const int fd = ::open(snp_locs_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+		const uint64_t n = snp_locs.size();
+		const bool ok = fd >= 0 && write_all(fd, &n, 8) && write_all(fd, snp_locs.data(), n);
+		if (fd >= 0) ::close(fd);
+		if (!ok) { fprintf(stderr, "vargeno-b200: cannot write %s\n", snp_locs_path.c_str()); return EXIT_FAILURE; }
+	}
 
 	if (!dump_parse.empty()) {
 		// host-side half only (no GPU needed): what the two VCF walks hand to the device builder, as text
@@ -277,6 +439,8 @@ int run_index(const std::string &fasta, const std::string &vcf_path, const std::
 		for (size_t c = 0; c < fa.names.size(); c++) fprintf(f, "C %s %llu %llu\n", fa.names[c].c_str(), (unsigned long long)fa.starts[c], (unsigned long long)fa.lens[c]);
 		for (size_t k = 0; k < sl.pos0.size(); k++) fprintf(f, "D %u %u %u %u\n", sl.pos0[k], sl.code[k], sl.rf[k], sl.af[k]);
 		for (size_t k = 0; k < sl.bf_pos0.size(); k++) fprintf(f, "B %u\n", sl.bf_pos0[k]);
+		for (size_t k = 0; k < ub.pos0.size(); k++) fprintf(f, "U %u %u\n", ub.pos0[k], ub.alt[k]);
+		if (!snp_locs.empty()) { uint64_t t = 0; for (uint8_t v : snp_locs) t += v; fprintf(f, "L %zu %llu\n", snp_locs.size(), (unsigned long long)t); }
 		fclose(f);
 		return EXIT_SUCCESS;
 	}
@@ -317,7 +481,19 @@ int run_index(const std::string &fasta, const std::string &vcf_path, const std::
 			if (!ok) { if (err.empty()) err = "cannot write " + prefix + ".snp.dict"; break; }
 		}
 		if (!write_bitvector(ctx, prefix + ".ref.bf", view.ref_bf_words, view.ref_bf_bits, view.ref_bf_nwords, buf, err)) break;
-		if (!write_bitvector(ctx, prefix + ".snp.bf", view.snp_bf_words, view.snp_bf_bits, view.snp_bf_nwords, buf, err)) break;
+		if (!ucsc) {
+			if (!write_bitvector(ctx, prefix + ".snp.bf", view.snp_bf_words, view.snp_bf_bits, view.snp_bf_nwords, buf, err)) break;
+		} else {
+			// UCSC input: the SNP filter holds 33 values per accepted record (src/generate_bf.cc:538-556), built by its own kernel
+			uint64_t *d_bf = nullptr, bits = 0, nw = 0;
+			if (vgb_build_snp_bf_ucsc_device(ctx, (const uint8_t *)d_genome, ub.pos0.data(), ub.alt.data(), ub.pos0.size(), &d_bf, &bits, &nw) != VGB_OK) {
+				err = vgb_last_error(ctx);
+				break;
+			}
+			const bool ok = write_bitvector(ctx, prefix + ".snp.bf", d_bf, bits, nw, buf, err);
+			vgb_device_free(ctx, d_bf);
+			if (!ok) break;
+		}
 		if (write_lite) {   // the sixth file of the reference's `index`
 			uint64_t *d_lite = nullptr, bits = 0, nw = 0;
 			if (vgb_build_ref_lite_bf_device(ctx, (const uint8_t *)d_genome, fa.starts.data(), fa.lens.data(), (uint32_t)fa.names.size(), &d_lite, &bits, &nw) != VGB_OK) {
@@ -342,6 +518,57 @@ int run_index(const std::string &fasta, const std::string &vcf_path, const std::
 	vgb_ctx_destroy(ctx);
 	printf("Time: %.2f sec\n", secs());
 	return status;
+}
+
+// `vargeno-b200 filt <ref.dict> <snp_locs> <out.dict>`: dict_filt, src/dict_filt.c:23-79 -- keeps the reference-dictionary entries
+// that are ambiguous or lie within a read length (READ_LEN 101, src/vartype.h:12) of a SNP; aux rows are copied as they are.
+int run_filt(const std::string &ref_dict, const std::string &snp_locs, const std::string &out_path)
+{
+	constexpr uint64_t READ_LEN = 101;
+	std::string err;
+	MappedFile rd, sl;
+	if (!rd.open(ref_dict, err) || !sl.open(snp_locs, err)) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+	if (sl.size < 8 || rd.size < 16) { fprintf(stderr, "vargeno-b200: truncated input\n"); return EXIT_FAILURE; }
+	uint64_t n_loc, n, an;
+	memcpy(&n_loc, sl.data, 8);
+	memcpy(&n, rd.data, 8);
+	memcpy(&an, rd.data + 8, 8);
+	if (sl.size < 8 + n_loc || rd.size < 16 + 13 * n + 40 * an) { fprintf(stderr, "vargeno-b200: truncated input\n"); return EXIT_FAILURE; }
+	if (n_loc < READ_LEN) { fprintf(stderr, "vargeno-b200: snp_locs table shorter than a read (the reference's window arithmetic wraps, src/dict_filt.c:15)\n"); return EXIT_FAILURE; }
+	const uint8_t *loc = sl.data + 8;
+	std::vector<uint32_t> pre(n_loc + 1, 0);            // pre[i] = number of SNP positions below i
+	for (uint64_t i = 0; i < n_loc; i++) pre[i + 1] = pre[i] + (loc[i] ? 1u : 0u);
+	FILE *out = fopen(out_path.c_str(), "wb");
+	if (!out) { fprintf(stderr, "vargeno-b200: cannot create %s\n", out_path.c_str()); return EXIT_FAILURE; }
+	uint64_t kept = 0;
+	fwrite(&kept, 8, 1, out);
+	fwrite(&an, 8, 1, out);
+	std::vector<uint8_t> buf;
+	buf.reserve(13u << 20);
+	const uint8_t *rec = rd.data + 16;
+	for (uint64_t i = 0; i < n; i++, rec += 13) {
+		uint32_t pos;
+		memcpy(&pos, rec + 8, 4);
+		bool keep = pos == 0xFFFFFFFFu || rec[12] == 1;
+		if (!keep && pos < n_loc) {
+			const uint64_t lo = pos > READ_LEN - 32 ? pos - (READ_LEN - 32) : 0;
+			const uint64_t hi = pos < n_loc - (READ_LEN - 1) ? pos + (READ_LEN - 1) : n_loc - 1;
+			keep = pre[hi + 1] != pre[lo];
+		}
+		if (keep) {
+			buf.insert(buf.end(), rec, rec + 13);
+			kept++;
+			if (buf.size() >= (13u << 20) - 13) { fwrite(buf.data(), 1, buf.size(), out); buf.clear(); }
+		}
+	}
+	fwrite(buf.data(), 1, buf.size(), out);
+	fwrite(rd.data + 16 + 13 * n, 1, 40 * an, out);
+	bool ok = fflush(out) == 0 && fseek(out, 0, SEEK_SET) == 0 && fwrite(&kept, 8, 1, out) == 1;
+	ok = (fclose(out) == 0) && ok;
+	if (!ok) { fprintf(stderr, "vargeno-b200: writing %s failed\n", out_path.c_str()); return EXIT_FAILURE; }
+	printf("New size: %llu\n", (unsigned long long)kept);
+	printf("Removed:  %llu/%llu\n", (unsigned long long)(n - kept), (unsigned long long)n);
+	return EXIT_SUCCESS;
 }
 
 }  // namespace vgh

@@ -16,6 +16,7 @@ static void print_help()
 	fprintf(stderr, "geno    Perform genotyping (B200)     <index_prefix> <input FASTQ> <input SNPs in VCF> <output file in VCF> "
 	                "[--gpus N] [--chunk-mb M] [--verbose]\n");
 	fprintf(stderr, "        (<input FASTQ>: one file or a comma-separated list read back to back; each plain or gzip)\n");
+	fprintf(stderr, "filt    Keep the reference-dictionary entries near SNPs   <ref.dict> <snp_locs> <out.dict>   (the reference's hidden `filt`)\n");
 	fprintf(stderr, "index   Build the index (B200)         <input FASTA> <input SNPs in VCF> <index_prefix> [--gpu D] [--no-lite] [--verbose]\n");
 	fprintf(stderr, "        (the same files as the reference's `vargeno index`, byte for byte; --no-lite skips the 2.3 GB .ref.bf.lite.bf that nothing reads)\n");
 }
@@ -40,19 +41,24 @@ int main(int argc, const char *argv[])
 		return vgh::run_geno(pos[0], pos[1], pos[2], pos[3], gpus, chunk_mb << 20, verbose);
 	}
 	if (opt == "index") {
-		std::string pos[3], dump;
+		std::string pos[3], dump, locs;
 		int npos = 0, dev = 0;
 		bool verbose = false, lite = true;
 		for (int i = 2; i < argc; i++) {
 			if (!strcmp(argv[i], "--gpu") && i + 1 < argc) dev = atoi(argv[++i]);
 			else if (!strcmp(argv[i], "--no-lite")) lite = false;
+			else if (!strcmp(argv[i], "--snp-locs") && i + 1 < argc) locs = argv[++i];
 			else if (!strcmp(argv[i], "--dump-parse") && i + 1 < argc) dump = argv[++i];
 			else if (!strcmp(argv[i], "--verbose")) verbose = true;
 			else if (npos < 3) pos[npos++] = argv[i];
 			else npos++;
 		}
 		if (npos != 3 || dev < 0) { print_help(); return EXIT_FAILURE; }   // arg_check, src/qv.cc:1875-1881
-		return vgh::run_index(pos[0], pos[1], pos[2], dev, verbose, dump, lite);
+		return vgh::run_index(pos[0], pos[1], pos[2], dev, verbose, dump, lite, locs);
+	}
+	if (opt == "filt") {              // dict_filt (src/qv.cc:2009-2025): <ref.dict> <snp_locs> <out.dict>
+		if (argc != 5) { print_help(); return EXIT_FAILURE; }
+		return vgh::run_filt(argv[2], argv[3], argv[4]);
 	}
 	if (opt == "fastq-chunks") {      // host-logic check, no GPU: how the FASTQ input would be cut into record-aligned chunks
 		std::string files;

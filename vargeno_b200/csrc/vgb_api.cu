@@ -433,6 +433,14 @@ int vgb_build_ref_lite_bf_device(vgb_ctx *c, const uint8_t *device_genome, const
 	return build_ref_lite_bf(c, device_genome, cstart, clen, n_contigs, device_words, bits, nwords);
 }
 
+int vgb_build_snp_bf_ucsc_device(vgb_ctx *c, const uint8_t *device_genome, const uint32_t *pos0, const uint8_t *alt_code, uint64_t n_lines,
+                                 uint64_t **device_words, uint64_t *bits, uint64_t *nwords)
+{
+	if (!c || !device_genome || !device_words || !bits || !nwords || (n_lines && (!pos0 || !alt_code))) return VGB_E_ARG;
+	cudaSetDevice(c->device);
+	return build_snp_bf_ucsc(c, device_genome, pos0, alt_code, n_lines, device_words, bits, nwords);
+}
+
 void vgb_free_index_device(vgb_ctx *c, vgb_index_view *view)
 {
 	if (!c || !view) return;

@@ -151,6 +151,53 @@ __global__ void __launch_bounds__(256) k_write_snp(const uint64_t *keys, const u
 	} else { st32u(r + 8, POS_AMBIGUOUS); r[12] = 0; r[13] = 1; r[14] = 0; r[15] = 0; }
 }
 
+// SNP Bloom filter from the UCSC table (constructBfFromUcsc, src/generate_bf.cc:538-556): per accepted record LO40 of the 32-mer that
+// ends just before the SNP -- inserted even when it holds an N, as the value 0 that encode_kmer returns (src/util.c:103) -- and then
+// LO40 of the 32 alternative-allele k-mers, up to the first N behind the SNP
+__global__ void __launch_bounds__(256) k_bf_snp_ucsc(const uint8_t *g, const uint32_t *pos0, const uint8_t *alt, uint64_t n, uint32_t *words32)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t p = pos0[i];
+	uint64_t km = 0;
+	bool had_n = false;
+	for (int j = 0; j < 32; j++) {
+		const uint32_t c = base2(g[p - 32 + j]);
+		if (c == 4) { had_n = true; break; }
+		km |= (uint64_t)c << (2 * j);
+	}
+	if (had_n) km = 0;
+	uint64_t bit = hash40(km & 0xFFFFFFFFFFull) % SNP_BF_BITS;
+	atomicOr(&words32[bit >> 5], 1u << (bit & 31));
+	if (had_n) return;
+	for (int j = 0; j < 32; j++) {
+		const uint32_t c = j ? base2(g[p + j]) : (uint32_t)alt[i];
+		if (c == 4) return;
+		km = (km >> 2) | ((uint64_t)c << 62);
+		bit = hash40(km & 0xFFFFFFFFFFull) % SNP_BF_BITS;
+		atomicOr(&words32[bit >> 5], 1u << (bit & 31));
+	}
+}
+
+int build_snp_bf_ucsc(vgb_ctx *c, const uint8_t *d_genome, const uint32_t *pos0, const uint8_t *alt, uint64_t n, uint64_t **d_words, uint64_t *bits, uint64_t *nwords)
+{
+	const uint64_t nw = (SNP_BF_BITS + 63) / 64;
+	uint32_t *w = nullptr, *d_pos = nullptr; uint8_t *d_alt = nullptr;
+	int rc;
+	if ((rc = dev_alloc(c, &w, nw * 2, false))) return rc;
+	if ((rc = dev_alloc(c, &d_pos, n, false)) || (rc = dev_alloc(c, &d_alt, n, false))) { cudaFree(w); cudaFree(d_pos); return rc; }
+	cudaError_t e = cudaMemsetAsync(w, 0, nw * 8, c->stream);
+	if (e == cudaSuccess && n) e = copy_sync(c, d_pos, pos0, n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && n) e = copy_sync(c, d_alt, alt, n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && n) { k_bf_snp_ucsc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_genome, d_pos, d_alt, n, w); c->launches++; }
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = cudaGetLastError();
+	cudaFree(d_pos); cudaFree(d_alt);
+	if (e != cudaSuccess) { cudaFree(w); return set_err(c, VGB_E_CUDA, "UCSC SNP filter build failed: %s", cudaGetErrorString(e)); }
+	*d_words = reinterpret_cast<uint64_t *>(w); *bits = SNP_BF_BITS; *nwords = nw;
+	return VGB_OK;
+}
+
 // <prefix>.ref.bf.lite.bf (src/generate_bf.cc:102-105,145-163): LO40 of every N-free 32-mer of every contig, value_range 40.
 // Written by the reference's `index`, read by nothing; produced here so that `index` leaves the same set of files behind.
 // Thread t owns the 32 k-mer starts cs + 32 t .. cs + 32 t + 31 (same walk as k_build_kmers).

@@ -140,6 +140,7 @@ int build_index_device(vgb_ctx *c, const uint8_t *d_genome, uint64_t genome_len,
                        const uint32_t *snp_pos0, const uint8_t *snp_code, const uint8_t *snp_rf, const uint8_t *snp_af, uint64_t n_snp_lines,
                        const uint32_t *bf_pos0, uint64_t n_bf_lines, vgb_index_view *out);
 void free_index_device(vgb_index_view *v);
+int build_snp_bf_ucsc(vgb_ctx *c, const uint8_t *d_genome, const uint32_t *pos0, const uint8_t *alt, uint64_t n, uint64_t **d_words, uint64_t *bits, uint64_t *nwords);
 int build_ref_lite_bf(vgb_ctx *c, const uint8_t *d_genome, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs,
                       uint64_t **d_words, uint64_t *bits, uint64_t *nwords);
 int synth_genome(vgb_ctx *c, uint8_t *d_out, const uint64_t *cstart, const uint64_t *clen, uint32_t n_contigs, uint64_t seed);

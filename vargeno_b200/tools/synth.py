@@ -229,6 +229,59 @@ def write_vcf(
         f.write("\n".join(out) + "\n")
 
 
+def write_ucsc_txt(genome: Genome, snps: SnpSet, path: str, seed: int = 0, adversarial: bool = True) -> None:
+    """UCSC snp141Common-style table dump (26 tab-separated columns; the legacy SNP input of the reference:
+    src/dictgen.c:350-540 make_snp_dict, src/generate_bf.cc:439-592 constructBfFromUcsc).  Columns the reference reads:
+    1 chrom, 2 chromStart (0-based), 6 strand, 7 refNCBI, 8 refUCSC, 9 observed, 11 class, 21 alleleFreqCount, 22 alleles,
+    24 alleleFreqs.  About a third of the records are on the '-' strand (alleles complemented, as UCSC prints them), the
+    allele order is shuffled (the frequency swap of :469-473), and with `adversarial` some records are of the kinds the
+    filters drop: not "single", three alleles, multi-base reference, refNCBI != refUCSC, unknown contig, neither allele equal
+    to the reference base, comment lines."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    out = ["#bin\tchrom\tchromStart\tchromEnd\tname\tscore\tstrand\trefNCBI\trefUCSC\tobserved\tmolType\tclass\tvalid\tavHet\tavHetSE\tfunc\t"
+           "locType\tweight\texceptions\tsubmitterCount\tsubmitters\talleleFreqCount\talleles\talleleNs\talleleFreqs\tbitfields"]
+
+    def row(chrom, start, strand, ref1, ref2, observed, klass, count, alleles, freqs, name):
+        return "\t".join(["585", chrom, str(start), str(start + 1), name, "0", strand, ref1, ref2, observed, "genomic", klass, "by-frequency",
+                          "0.3", "0.1", "intron", "exact", "1", "", "2", "A,B,", str(count), alleles, "10.0,20.0,", freqs, "maf-5-some-pop"])
+
+    for i in range(snps.pos0.size):
+        r = int(rnd64(seed, 70, i))
+        name = genome.names[int(snps.contig[i])]
+        ref, alt = chr(snps.ref[i]), chr(snps.alt[i])
+        cr = float(snps.caf_ref[i])
+        f_ref, f_alt = repr(round(1.0 - cr, 6)), repr(cr)
+        neg = (r % 3) == 0
+        a, b = (comp[ref], comp[alt]) if neg else (ref, alt)
+        fa, fb = f_ref, f_alt
+        if (r >> 8) & 1:
+            a, b, fa, fb = b, a, fb, fa
+        observed = "/".join(sorted([a, b]))
+        start = int(snps.pos0[i])
+        out.append(row(name, start, "-" if neg else "+", ref, ref, observed, "single", 2, a + "," + b + ",", fa + "," + fb + ",", "rs%d" % (i + 1)))
+        if adversarial and i % 23 == 0:
+            kind = (i // 23) % 7
+            nxt = chr(genome.seqs[int(snps.contig[i])][start + 1]) if start + 1 < genome.seqs[int(snps.contig[i])].size else "A"
+            others = [x for x in "ACGT" if x not in (ref, alt)]
+            if kind == 0:
+                out.append(row(name, start, "+", ref, ref, "-/" + ref, "deletion", 2, "-," + ref + ",", "0.5,0.5,", "rsD%d" % i))
+            elif kind == 1:
+                out.append(row(name, start, "+", ref, ref, "/".join(sorted([ref, alt, others[0]])), "single", 3,
+                               ",".join([ref, alt, others[0]]) + ",", "0.5,0.25,0.25,", "rsT%d" % i))
+            elif kind == 2 and nxt in "ACGT":
+                out.append(row(name, start, "+", ref + nxt, ref + nxt, ref + nxt + "/" + ref, "in-del", 2, ref + nxt + "," + ref + ",", "0.5,0.5,", "rsM%d" % i))
+            elif kind == 3:
+                out.append(row(name, start, "+", ref, others[0], observed, "single", 2, a + "," + b + ",", fa + "," + fb + ",", "rsR%d" % i))
+            elif kind == 4:
+                out.append(row("chrUn_gl000%d" % (i % 9), start, "+", ref, ref, observed, "single", 2, a + "," + b + ",", fa + "," + fb + ",", "rsU%d" % i))
+            elif kind == 5:
+                out.append(row(name, start, "+", ref, ref, "/".join(sorted(others)), "single", 2, others[0] + "," + others[1] + ",", "0.5,0.5,", "rsX%d" % i))
+            else:
+                out.append("# a comment line in the middle of the table")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+
+
 def donor_haplotypes(genome: Genome, snps: SnpSet, seed: int) -> Tuple[np.ndarray, np.ndarray]:
     """Two concatenated haplotype sequences of the donor (alt applied per genotype)."""
     cat = genome.concat()
