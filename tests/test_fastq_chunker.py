@@ -110,3 +110,39 @@ def test_parallel_pread_gives_the_same_chunks(tmp_path):
         outs.append(p.stdout)
     assert outs[0] == outs[1]
     assert outs[0].strip().splitlines()[-1].startswith("total %d bytes" % (60 * len(block)))
+
+
+@pytest.mark.parametrize("feeders", [1, 3, 8])
+@pytest.mark.parametrize("chunk_bytes", [300_000, 1 << 20, 1 << 23])
+@pytest.mark.parametrize("layout", ["one_file", "three_files_cut_mid_record", "no_trailing_newline"])
+def test_parallel_reader_tiles_the_input_with_whole_records(tmp_path, feeders, chunk_bytes, layout):
+    """The per-GPU feeders of plain files (stream_plain_parallel): segments are claimed independently, record starts are found
+    locally ('@' at a line start whose second next line starts with '+': every seventh quality line here starts with '@'), and
+    the chunks must tile the input exactly -- whatever the segment size, the number of feeders and the file boundaries."""
+    vb.build()
+    text = _fastq(6000, seed=9, trailing_newline=layout != "no_trailing_newline")
+    if layout == "three_files_cut_mid_record":
+        cut = len(text) // 3 + 11
+        parts = [text[:cut], text[cut:2 * cut], text[2 * cut:]]
+    else:
+        parts = [text]
+    names = []
+    for i, part in enumerate(parts):
+        f = tmp_path / ("p%d.fq" % i)
+        f.write_bytes(part)
+        names.append(str(f))
+    p = subprocess.run([vb.HOST_BIN, "fastq-chunks", ",".join(names), "--chunk-bytes", str(chunk_bytes), "--parallel", str(feeders)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    rows = sorted([int(x, 16) if k == 3 else int(x) for k, x in enumerate(l.split())] for l in p.stdout.splitlines() if not l.startswith("total"))
+    assert len(rows) >= 1
+    at = 0
+    for off, nbytes, lines, h in rows:
+        assert off == at, "gap or overlap at byte %d" % at
+        piece = text[off:off + nbytes]
+        assert piece[:1] == b"@" and _fnv(piece) == h
+        n_lines = piece.count(b"\n") + (0 if piece.endswith(b"\n") else 1)
+        assert n_lines % 4 == 0                                    # whole records only
+        at += nbytes
+    assert at == len(text)
+    assert len(rows) >= min(3, len(text) // chunk_bytes)

@@ -11,12 +11,14 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <thread>
 
 namespace vgh {
@@ -234,9 +236,158 @@ struct GpuSink : ChunkSink {
 };
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Plain regular files: the concatenation is one byte range of known length, so it is cut into segments up front and every
+// GPU gets its own feeder (a coordinator + its share of the reading threads + its own pinned pair) -- no feeder waits for
+// another, nothing is carried from one chunk to the next.  Segment k is [k S, (k + 1) S); its chunk runs from the first record
+// start at or after k S to the first record start at or after (k + 1) S.  A record start is recognised locally: an '@' at the
+// beginning of a line whose second next line begins with '+' (a quality line may begin with '@' too, but then the second
+// next line is a sequence line, which cannot begin with '+').
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct PlainSet {
+	std::vector<int> fds;
+	std::vector<uint64_t> start;      // offset of file i in the concatenation; start[n] = total
+	std::vector<std::string> names;
+	~PlainSet() { for (int fd : fds) if (fd >= 0) ::close(fd); }
+	// all paths plain regular files?  (gzip members and pipes go through the sequential reader)
+	bool open(const std::vector<std::string> &paths)
+	{
+		start.assign(1, 0);
+		for (const std::string &p : paths) {
+			const int fd = ::open(p.c_str(), O_RDONLY);
+			if (fd < 0) return false;
+			fds.push_back(fd);
+			struct stat st;
+			unsigned char magic[2] = { 0, 0 };
+			if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+			if (::pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) return false;
+			posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+			start.push_back(start.back() + (uint64_t)st.st_size);
+			names.push_back(p);
+		}
+		return !fds.empty();
+	}
+	uint64_t total() const { return start.back(); }
+	// bytes [pos, pos + n) of the concatenation into dst; false on a read error
+	bool read(char *dst, uint64_t pos, uint64_t n) const
+	{
+		size_t i = (size_t)(std::upper_bound(start.begin(), start.end(), pos) - start.begin()) - 1;
+		while (n) {
+			if (i + 1 >= start.size()) return false;
+			const uint64_t in_file = pos - start[i], avail = start[i + 1] - pos;
+			if (avail == 0) { i++; continue; }
+			const uint64_t want = std::min(n, avail);
+			const ssize_t r = ::pread(fds[i], dst, want, (off_t)in_file);
+			if (r <= 0) return false;
+			dst += r; pos += (uint64_t)r; n -= (uint64_t)r;
+		}
+		return true;
+	}
+};
+
+// first record start at or after buffer offset `from` (buf[from - 1] must exist unless abs0 + from == 0); n = bytes in buf.
+// Returns n when there is none (the caller decides whether that is the end of the input or an error).
+uint64_t record_start(const char *buf, uint64_t n, uint64_t from, bool at_file_start)
+{
+	uint64_t r = from;
+	if (!(at_file_start && r == 0)) {
+		// move to the beginning of a line: r is a line start iff buf[r - 1] == '\n'
+		while (r < n && buf[r - 1] != '\n') r++;
+	}
+	while (r < n) {
+		if (buf[r] == '@') {
+			const char *l1 = (const char *)memchr(buf + r, '\n', n - r);
+			const char *l2 = l1 ? (const char *)memchr(l1 + 1, '\n', (size_t)(buf + n - (l1 + 1))) : nullptr;
+			if (l2 && l2 + 1 < buf + n && l2[1] == '+') return r;
+			if (!l2 || l2 + 1 >= buf + n) return n;              // not enough bytes behind it to tell
+		}
+		const char *nl = (const char *)memchr(buf + r, '\n', n - r);
+		if (!nl) return n;
+		r = (uint64_t)(nl - buf) + 1;
+	}
+	return n;
+}
+
+// sink: chunk number `turn` = g + n_feeders * j is the j-th chunk of feeder g (GpuSink: context g, pinned slot j & 1); `first_read`
+// of submit() carries the chunk's byte offset in the input here (read ordinals are not known without a global pass, and nothing
+// downstream needs them)
+int stream_plain_parallel(ChunkSink &sink, size_t n_feeders, const PlainSet &in, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
+{
+	constexpr uint64_t SLACK = 1u << 16;                        // a record is at most 4 lines of <= 1023 characters
+	if (chunk_bytes <= 4 * SLACK) { err = "chunk size too small for the parallel reader"; return VGB_E_ARG; }
+	const uint64_t S = chunk_bytes - 2 * SLACK, total = in.total();
+	const uint64_t n_seg = (total + S - 1) / S;
+	int per_gpu;
+	{
+		const char *e = getenv("VGB_READ_THREADS");
+		const int hw = (int)std::thread::hardware_concurrency();
+		per_gpu = e ? atoi(e) : std::max(1, std::min(16, (hw > 0 ? hw : 1) / (int)n_feeders));
+		if (per_gpu < 1) per_gpu = 1;
+	}
+	std::atomic<uint64_t> next(0), chunks(0);
+	std::atomic<int> failed(0);
+	std::vector<std::string> errs(n_feeders);
+	std::vector<int> rcs(n_feeders, VGB_OK);
+	auto feeder = [&](size_t g) {
+		size_t j = 0;                                           // chunks this feeder has submitted
+		for (;;) {
+			const uint64_t k = next.fetch_add(1);
+			if (k >= n_seg || failed.load()) break;
+			const uint64_t a = k * S, b = std::min(total, a + S);
+			const uint64_t a0 = a ? a - 1 : 0, b1 = std::min(total, b + SLACK);
+			char *buf = nullptr;
+			uint64_t cap = 0;
+			const size_t turn = g + n_feeders * j;
+			if ((rcs[g] = sink.buffer(turn, &buf, &cap, errs[g])) != VGB_OK) { failed = 1; break; }
+			const uint64_t len = b1 - a0;
+			if (len > cap) { errs[g] = "pinned buffer smaller than a segment"; rcs[g] = VGB_E_ARG; failed = 1; break; }
+			// the segment, read by this feeder's share of the threads
+			{
+				const uint64_t part = (len + per_gpu - 1) / per_gpu;
+				std::vector<std::thread> th;
+				std::atomic<int> bad(0);
+				for (int t = 1; t < per_gpu; t++) {
+					const uint64_t x = std::min<uint64_t>((uint64_t)t * part, len), y = std::min<uint64_t>(x + part, len);
+					if (x < y) th.emplace_back([&, x, y]() { if (!in.read(buf + x, a0 + x, y - x)) bad = 1; });
+				}
+				if (!in.read(buf, a0, std::min(part, len))) bad = 1;
+				for (auto &x : th) x.join();
+				if (bad.load()) { errs[g] = "read error on the FASTQ input"; rcs[g] = VGB_E_ARG; failed = 1; break; }
+			}
+			const uint64_t s0 = record_start(buf, len, a - a0, a == 0);
+			uint64_t s1 = len;
+			if (b < total) {
+				s1 = record_start(buf, len, b - a0, false);
+				if (s1 == len && b1 < total) { errs[g] = "no FASTQ record boundary within 64 KiB of a segment end (record framing is broken)"; rcs[g] = VGB_E_FORMAT; failed = 1; break; }
+			}
+			if (s0 >= s1) continue;                             // the whole segment lies inside one record of the neighbour
+			if ((rcs[g] = sink.submit(turn, buf + s0, s1 - s0, a0 + s0, errs[g])) != VGB_OK) { failed = 1; break; }
+			chunks++;
+			j++;
+		}
+	};
+	std::vector<std::thread> th;
+	for (size_t g = 0; g < n_feeders; g++) th.emplace_back(feeder, g);
+	for (auto &t : th) t.join();
+	n_chunks = chunks.load();
+	for (size_t g = 0; g < n_feeders; g++) if (rcs[g] != VGB_OK) { err = errs[g]; return rcs[g]; }
+	return VGB_OK;
+}
+}  // namespace
+
 int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
 {
+	std::vector<std::string> paths;
+	{
+		size_t a = 0, b;
+		while ((b = path.find(',', a)) != std::string::npos) { if (b > a) paths.push_back(path.substr(a, b - a)); a = b + 1; }
+		if (a < path.size()) paths.push_back(path.substr(a));
+	}
+	PlainSet plain;
 	GpuSink sink(ctxs);
+	if (!paths.empty() && !getenv("VGB_SEQUENTIAL_READER") && plain.open(paths) && plain.total() > 0)
+		return stream_plain_parallel(sink, ctxs.size(), plain, chunk_bytes, n_chunks, err);
 	return stream_fastq_to(sink, path, chunk_bytes, n_chunks, err);
 }
 
@@ -305,8 +456,52 @@ int stream_fastq_to(ChunkSink &sink, const std::string &path, uint64_t chunk_byt
 }
 
 // `vargeno-b200 fastq-chunks`: the chunker alone, no GPU -- one line per chunk (bytes, lines, first read, FNV-1a of the bytes)
-int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes, bool timing)
+int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes, bool timing, int parallel)
 {
+	if (parallel > 0) {
+		// the per-GPU parallel reader of plain files with `parallel` feeders and no GPU: one line per chunk
+		// (byte offset in the input, bytes, lines, FNV-1a), in no particular order; --time prints the throughput instead
+		struct ParSink : ChunkSink {
+			std::vector<std::vector<char>> mem;                 // two buffers per feeder, as the GPU contexts have
+			size_t n;
+			bool quiet;
+			std::atomic<uint64_t> total{0};
+			std::mutex mu;
+			ParSink(size_t n_, uint64_t cap, bool q) : mem(2 * n_, std::vector<char>(cap)), n(n_), quiet(q) {}
+			int buffer(size_t turn, char **buf, uint64_t *cap, std::string &) override
+			{
+				std::vector<char> &m = mem[2 * (turn % n) + ((turn / n) & 1)];
+				*buf = m.data(); *cap = m.size();
+				return VGB_OK;
+			}
+			int submit(size_t, const char *buf, uint64_t nbytes, uint64_t offset, std::string &) override
+			{
+				total += nbytes;
+				if (quiet) return VGB_OK;
+				uint64_t h = 1469598103934665603ull;
+				for (uint64_t i = 0; i < nbytes; i++) { h ^= (unsigned char)buf[i]; h *= 1099511628211ull; }
+				std::lock_guard<std::mutex> lk(mu);
+				printf("%llu %llu %llu %016llx\n", (unsigned long long)offset, (unsigned long long)nbytes, (unsigned long long)count_newlines(buf, nbytes), (unsigned long long)h);
+				return VGB_OK;
+			}
+		} sink((size_t)parallel, chunk_bytes, timing);
+		std::vector<std::string> paths;
+		size_t a = 0, b;
+		while ((b = fastq.find(',', a)) != std::string::npos) { if (b > a) paths.push_back(fastq.substr(a, b - a)); a = b + 1; }
+		if (a < fastq.size()) paths.push_back(fastq.substr(a));
+		PlainSet plain;
+		if (!plain.open(paths)) { fprintf(stderr, "vargeno-b200: the parallel reader takes plain regular files only\n"); return EXIT_FAILURE; }
+		uint64_t n_chunks = 0;
+		std::string err;
+		const auto t0 = std::chrono::steady_clock::now();
+		const int rc = stream_plain_parallel(sink, (size_t)parallel, plain, chunk_bytes, n_chunks, err);
+		const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (rc != VGB_OK) { fprintf(stderr, "vargeno-b200: %s\n", err.c_str()); return EXIT_FAILURE; }
+		if (timing) printf("{\"bytes\": %llu, \"chunks\": %llu, \"feeders\": %d, \"seconds\": %.4f, \"gb_per_s\": %.3f}\n", (unsigned long long)sink.total.load(),
+		                   (unsigned long long)n_chunks, parallel, sec, sink.total.load() / sec / 1e9);
+		else printf("total %llu bytes in %llu chunks\n", (unsigned long long)sink.total.load(), (unsigned long long)n_chunks);
+		return EXIT_SUCCESS;
+	}
 	if (timing) {
 		// reader throughput alone: chunks are assembled and dropped (VGB_READ_THREADS sets the parallel pread count)
 		struct NullSink : ChunkSink {

@@ -48,7 +48,7 @@ struct ChunkSink {
 	virtual ~ChunkSink() {}
 };
 int stream_fastq_to(ChunkSink &sink, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err);
-int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes, bool timing = false);   // `vargeno-b200 fastq-chunks <files> [--chunk-bytes B] [--time]`
+int run_fastq_chunks(const std::string &fastq, uint64_t chunk_bytes, bool timing = false, int parallel = 0);   // `vargeno-b200 fastq-chunks <files> [--chunk-bytes B] [--time] [--parallel N]`
 
 // stage F on the host side: device calls -> "chr$pos" -> (gt, conf) map (src/qv.cc:1596-1621)
 int collect_calls(vgb_ctx *ctx, const ChrLens &chr, std::unordered_map<std::string, Call> &out, std::string &err);

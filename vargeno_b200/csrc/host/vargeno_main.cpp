@@ -64,14 +64,16 @@ int main(int argc, const char *argv[])
 		std::string files;
 		uint64_t bytes = 256ull << 20;
 		bool timing = false;
+		int parallel = 0;
 		for (int i = 2; i < argc; i++) {
 			if (!strcmp(argv[i], "--time")) timing = true;
+			else if (!strcmp(argv[i], "--parallel") && i + 1 < argc) parallel = atoi(argv[++i]);
 			else if (!strcmp(argv[i], "--chunk-bytes") && i + 1 < argc) bytes = strtoull(argv[++i], nullptr, 10);
 			else if (!strcmp(argv[i], "--chunk-mb") && i + 1 < argc) bytes = strtoull(argv[++i], nullptr, 10) << 20;
 			else files = argv[i];
 		}
 		if (files.empty() || bytes < 16) { print_help(); return EXIT_FAILURE; }
-		return vgh::run_fastq_chunks(files, bytes, timing);
+		return vgh::run_fastq_chunks(files, bytes, timing, parallel);
 	}
 	if (opt == "vcf-rewrite") {       // host-logic check, no GPU: chrlens mapping + GQ + VCF rewrite from a table of calls
 		if (argc != 6) { print_help(); return EXIT_FAILURE; }

@@ -215,7 +215,8 @@ static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_
 		VGB_CUDA(c, cudaMemcpyAsync(k.d_text, host_chunk, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
 		VGB_CUDA(c, cudaEventRecord(k.copied, c->copy_stream));
 		VGB_CUDA(c, cudaStreamWaitEvent(c->stream, k.copied, 0));
-		if (host_chunk != k.h_pinned && host_chunk != c->chunk[slot ^ 1].h_pinned)
+		auto in_pinned = [&](const Chunk &q) { return q.h_pinned && host_chunk >= q.h_pinned && host_chunk < q.h_pinned + c->max_chunk_bytes; };
+		if (!in_pinned(k) && !in_pinned(c->chunk[slot ^ 1]))
 			VGB_CUDA(c, cudaEventSynchronize(k.copied));   // caller's own memory: safe to reuse on return
 	}
 	VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));
