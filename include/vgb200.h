@@ -141,6 +141,17 @@ int  vgb_fetch_sites(vgb_ctx *ctx, uint32_t *pos, uint8_t *code, uint8_t *ref_fr
 int  vgb_pinned_buffer(vgb_ctx *ctx, int slot, char **ptr, uint64_t *capacity);   /* slot 0 or 1; waits until the slot is free */
 int  vgb_submit_fastq(vgb_ctx *ctx, const char *chunk, uint64_t nbytes, uint64_t first_read_id);
 int  vgb_submit_fastq_device(vgb_ctx *ctx, const char *device_chunk, uint64_t nbytes, uint64_t first_read_id);
+/* BGZF input (blocked gzip, as bgzip / htslib write it): the gzip members of a chunk go over PCIe compressed and are inflated
+ * on the device, one warp per member.  `comp` holds the members back to back (host memory; a vgb_pinned_buffer is copied without
+ * staging), members[i] locates the raw DEFLATE payload of member i inside it and gives its ISIZE.  A chunk is a run of whole
+ * members, so it may begin and end inside a record: the caller puts the last members of the previous chunk (at least 8 KiB of
+ * text, or everything back to the start of the input) in front again and passes their inflated size as overlap_bytes -- the
+ * chunk then processes exactly the records that end behind that point.  last_chunk: the input ends with this chunk (a trailing
+ * partial record is a format error instead of the next chunk's business).  CRC32 of the members is not verified; a member that
+ * does not inflate to its ISIZE is reported by vgb_sync as VGB_E_FORMAT. */
+typedef struct { uint32_t comp_offset, comp_len, out_len; } vgb_bgzf_member;
+int  vgb_submit_bgzf(vgb_ctx *ctx, const void *comp, uint64_t comp_bytes, const vgb_bgzf_member *members, uint32_t n_members,
+                     uint64_t overlap_bytes, int last_chunk);
 int  vgb_sync(vgb_ctx *ctx);
 int  vgb_reset_counts(vgb_ctx *ctx);              /* zero the pileup counters, statistics and the trace */
 int  vgb_fetch_read_results(vgb_ctx *ctx, vgb_read_result *out, uint64_t cap, uint64_t *n);   /* needs VGB_CFG_TRACE */

@@ -376,6 +376,138 @@ int stream_plain_parallel(ChunkSink &sink, size_t n_feeders, const PlainSet &in,
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// BGZF (blocked gzip: bgzip, htslib): every file is a series of gzip members of at most 64 KiB that carry their own size, so the
+// member table is built by walking the headers, chunks are runs of whole members, and the members are inflated ON THE DEVICE
+// (vgb_submit_bgzf): the compressed bytes are all that crosses PCIe.  A chunk starts with the last >= 8 KiB of text of the
+// previous one (its `overlap`), so that the record cut by the chunk boundary is whole in the chunk that owns it.  Feeders as for
+// plain files: one per GPU, chunks claimed through a counter.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct BgzfMember { uint32_t file; uint64_t off; uint32_t size, payload_off, payload_len, isize; };   // member = [off, off + size) of its file
+
+// every file a well-formed BGZF file?  Fills the member table (empty members -- the EOF marker -- are left out).
+bool bgzf_scan(const std::vector<std::string> &paths, std::vector<MappedFile> &files, std::vector<BgzfMember> &mem)
+{
+	files.resize(paths.size());
+	for (size_t f = 0; f < paths.size(); f++) {
+		std::string e;
+		if (!files[f].open(paths[f], e) || files[f].size < 28) return false;
+		const uint8_t *d = files[f].data;
+		const uint64_t n = files[f].size;
+		uint64_t off = 0;
+		while (off < n) {
+			if (off + 18 > n || d[off] != 0x1f || d[off + 1] != 0x8b || d[off + 2] != 8 || !(d[off + 3] & 4)) return false;
+			const uint32_t xlen = d[off + 10] | (d[off + 11] << 8);
+			if (off + 12 + xlen > n) return false;
+			uint32_t bsize = 0;
+			for (uint32_t x = 0; x + 4 <= xlen;) {              // extra subfields: SI1 SI2 SLEN(2) data
+				const uint8_t *sf = d + off + 12 + x;
+				const uint32_t slen = sf[2] | (sf[3] << 8);
+				if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (sf[4] | (sf[5] << 8)) + 1u;
+				x += 4 + slen;
+			}
+			if (bsize < 12 + xlen + 8 || off + bsize > n || (d[off + 3] & ~4u)) return false;   // no BC field, or other optional header parts
+			BgzfMember m;
+			m.file = (uint32_t)f; m.off = off; m.size = bsize; m.payload_off = 12 + xlen; m.payload_len = bsize - (12 + xlen) - 8;
+			memcpy(&m.isize, d + off + bsize - 4, 4);
+			if (m.isize > 65536) return false;
+			if (m.isize) mem.push_back(m);
+			off += bsize;
+		}
+	}
+	return !mem.empty();
+}
+
+struct BgzfChunk { size_t o0, i0, i1; uint64_t ov; };      // members [o0, i0) overlap, [i0, i1) own; ov = inflated size of the overlap
+
+int stream_bgzf(const std::vector<vgb_ctx *> &ctxs, const std::vector<MappedFile> &files, const std::vector<BgzfMember> &mem, uint64_t chunk_bytes,
+                uint64_t &n_chunks, std::string &err)
+{
+	constexpr uint64_t OVERLAP = 8192;                          // > one record (4 lines of <= 1023 characters)
+	if (chunk_bytes < (1u << 20)) { err = "chunk size too small for BGZF input (1 MiB at least)"; return VGB_E_ARG; }
+	const uint64_t own_out = chunk_bytes - (OVERLAP + 65536) - 4096;
+	std::vector<BgzfChunk> plan;
+	for (size_t i = 0; i < mem.size();) {
+		BgzfChunk c;
+		c.i0 = i;
+		uint64_t out = 0, comp = 0;
+		while (i < mem.size() && out + mem[i].isize <= own_out && comp + mem[i].size <= chunk_bytes / 2) { out += mem[i].isize; comp += mem[i].size; i++; }
+		c.i1 = i;
+		c.o0 = c.i0; c.ov = 0;
+		while (c.o0 > 0 && c.ov < OVERLAP) { c.o0--; c.ov += mem[c.o0].isize; }
+		plan.push_back(c);
+	}
+	int per_gpu;
+	{
+		const char *e = getenv("VGB_READ_THREADS");
+		const int hw = (int)std::thread::hardware_concurrency();
+		per_gpu = e ? atoi(e) : std::max(1, std::min(8, (hw > 0 ? hw : 1) / (int)ctxs.size()));
+		if (per_gpu < 1) per_gpu = 1;
+	}
+	std::atomic<size_t> next(0);
+	std::atomic<int> failed(0);
+	std::vector<std::string> errs(ctxs.size());
+	std::vector<int> rcs(ctxs.size(), VGB_OK);
+	auto feeder = [&](size_t g) {
+		vgb_ctx *ctx = ctxs[g];
+		int slot = 0;
+		std::vector<vgb_bgzf_member> tab;
+		struct Job { const uint8_t *src; uint64_t dst, len; };
+		std::vector<Job> jobs;
+		for (;;) {
+			const size_t k = next.fetch_add(1);
+			if (k >= plan.size() || failed.load()) break;
+			const BgzfChunk &c = plan[k];
+			char *buf = nullptr;
+			uint64_t cap = 0;
+			if ((rcs[g] = vgb_pinned_buffer(ctx, slot, &buf, &cap)) != VGB_OK) { errs[g] = vgb_last_error(ctx); failed = 1; break; }
+			// the members, back to back in the pinned buffer (runs of neighbours in a file are one copy job)
+			tab.clear(); jobs.clear();
+			uint64_t at = 0;
+			for (size_t i = c.o0; i < c.i1; i++) {
+				const BgzfMember &m = mem[i];
+				const uint8_t *src = files[m.file].data + m.off;
+				if (!jobs.empty() && jobs.back().src + jobs.back().len == src) jobs.back().len += m.size;
+				else jobs.push_back(Job{ src, at, m.size });
+				tab.push_back(vgb_bgzf_member{ (uint32_t)(at + m.payload_off), m.payload_len, m.isize });
+				at += m.size;
+			}
+			if (at > cap) { errs[g] = "pinned buffer smaller than a BGZF chunk"; rcs[g] = VGB_E_ARG; failed = 1; break; }
+			{
+				// split the bytes evenly over this feeder's threads
+				const uint64_t part = (at + per_gpu - 1) / per_gpu;
+				auto copy_range = [&](uint64_t x, uint64_t y) {
+					for (const Job &j : jobs) {
+						const uint64_t a = std::max(x, j.dst), b = std::min(y, j.dst + j.len);
+						if (a < b) memcpy(buf + a, j.src + (a - j.dst), b - a);
+					}
+				};
+				std::vector<std::thread> th;
+				for (int t = 1; t < per_gpu; t++) {
+					const uint64_t x = std::min<uint64_t>((uint64_t)t * part, at), y = std::min<uint64_t>(x + part, at);
+					if (x < y) th.emplace_back(copy_range, x, y);
+				}
+				copy_range(0, std::min(part, at));
+				for (auto &x : th) x.join();
+			}
+			if ((rcs[g] = vgb_submit_bgzf(ctx, buf, at, tab.data(), (uint32_t)tab.size(), c.ov, k + 1 == plan.size())) != VGB_OK) {
+				errs[g] = vgb_last_error(ctx);
+				failed = 1;
+				break;
+			}
+			slot ^= 1;
+		}
+	};
+	std::vector<std::thread> th;
+	for (size_t g = 0; g < ctxs.size(); g++) th.emplace_back(feeder, g);
+	for (auto &t : th) t.join();
+	n_chunks = plan.size();
+	for (size_t g = 0; g < ctxs.size(); g++) if (rcs[g] != VGB_OK) { err = errs[g]; return rcs[g]; }
+	return VGB_OK;
+}
+}  // namespace
+
 int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, uint64_t chunk_bytes, uint64_t &n_chunks, std::string &err)
 {
 	std::vector<std::string> paths;
@@ -388,6 +520,12 @@ int stream_fastq(const std::vector<vgb_ctx *> &ctxs, const std::string &path, ui
 	GpuSink sink(ctxs);
 	if (!paths.empty() && !getenv("VGB_SEQUENTIAL_READER") && plain.open(paths) && plain.total() > 0)
 		return stream_plain_parallel(sink, ctxs.size(), plain, chunk_bytes, n_chunks, err);
+	{
+		std::vector<MappedFile> files;
+		std::vector<BgzfMember> mem;
+		if (!paths.empty() && !getenv("VGB_SEQUENTIAL_READER") && !getenv("VGB_HOST_INFLATE") && bgzf_scan(paths, files, mem))
+			return stream_bgzf(ctxs, files, mem, chunk_bytes, n_chunks, err);
+	}
 	return stream_fastq_to(sink, path, chunk_bytes, n_chunks, err);
 }
 

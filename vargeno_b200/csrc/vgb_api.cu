@@ -194,33 +194,11 @@ static void collect_times(vgb_ctx *c, int slot)
 	k.busy = false;
 }
 
-static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_chunk, uint64_t nbytes, uint64_t first_read_id)
+// the text of the chunk is (or will be, in stream order) in k.d_text: record framing, then the per-read kernels
+static int process_text(vgb_ctx *c, Chunk &k, uint64_t nbytes, uint64_t first_read_id, int window, uint64_t ov, int last)
 {
-	if (!c) return VGB_E_ARG;
-	if (!c->have_index) return set_err(c, VGB_E_ARG, "vgb_index_upload has not been called");
-	if (nbytes > c->max_chunk_bytes) return set_err(c, VGB_E_ARG, "chunk of %llu bytes exceeds max_chunk_bytes %llu", (unsigned long long)nbytes, (unsigned long long)c->max_chunk_bytes);
-	if (nbytes == 0) return VGB_OK;
-	cudaSetDevice(c->device);
-	const int slot = c->next_slot;
-	c->next_slot ^= 1;
-	Chunk &k = c->chunk[slot];
-	collect_times(c, slot);                            // waits until the previous chunk in this slot is done
-	char *own_text = k.d_text;
-	// Two streams: the H2D copy of chunk i+1 runs under the kernels of chunk i.  Record framing stays on the kernel stream:
-	// k_geno8 is a persistent grid that fills every SM, so a framing kernel on a third stream only gets the SMs when k_geno8
-	// drains (measured: 1.5 % on the step, and both kernels' event times stop meaning anything).
-	if (device_chunk) {
-		k.d_text = const_cast<char *>(device_chunk);   // resident input: no copy at all
-	} else {
-		VGB_CUDA(c, cudaMemcpyAsync(k.d_text, host_chunk, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
-		VGB_CUDA(c, cudaEventRecord(k.copied, c->copy_stream));
-		VGB_CUDA(c, cudaStreamWaitEvent(c->stream, k.copied, 0));
-		auto in_pinned = [&](const Chunk &q) { return q.h_pinned && host_chunk >= q.h_pinned && host_chunk < q.h_pinned + c->max_chunk_bytes; };
-		if (!in_pinned(k) && !in_pinned(c->chunk[slot ^ 1]))
-			VGB_CUDA(c, cudaEventSynchronize(k.copied));   // caller's own memory: safe to reuse on return
-	}
 	VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));
-	int rc = fastq_index_lines(c, k, nbytes, c->stream);
+	int rc = fastq_index_lines(c, k, nbytes, c->stream, window, ov, last);
 	if (rc == VGB_OK) {
 		VGB_CUDA(c, cudaEventRecord(k.t1, c->stream));
 		if (c->cfg.flags & VGB_CFG_TRACE) {
@@ -248,11 +226,82 @@ static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_
 	}
 	cudaEventRecord(k.done, c->stream);
 	k.busy = true;
-
-	if (device_chunk) k.d_text = own_text;
 	c->chunks++;
 	c->chunk_bytes += nbytes;
 	return rc;
+}
+
+static int submit_common(vgb_ctx *c, const char *host_chunk, const char *device_chunk, uint64_t nbytes, uint64_t first_read_id)
+{
+	if (!c) return VGB_E_ARG;
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "vgb_index_upload has not been called");
+	if (nbytes > c->max_chunk_bytes) return set_err(c, VGB_E_ARG, "chunk of %llu bytes exceeds max_chunk_bytes %llu", (unsigned long long)nbytes, (unsigned long long)c->max_chunk_bytes);
+	if (nbytes == 0) return VGB_OK;
+	cudaSetDevice(c->device);
+	const int slot = c->next_slot;
+	c->next_slot ^= 1;
+	Chunk &k = c->chunk[slot];
+	collect_times(c, slot);                            // waits until the previous chunk in this slot is done
+	char *own_text = k.d_text;
+	// Two streams: the H2D copy of chunk i+1 runs under the kernels of chunk i.  Record framing stays on the kernel stream:
+	// k_geno8 is a persistent grid that fills every SM, so a framing kernel on a third stream only gets the SMs when k_geno8
+	// drains (measured: 1.5 % on the step, and both kernels' event times stop meaning anything).
+	if (device_chunk) {
+		k.d_text = const_cast<char *>(device_chunk);   // resident input: no copy at all
+	} else {
+		VGB_CUDA(c, cudaMemcpyAsync(k.d_text, host_chunk, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+		VGB_CUDA(c, cudaEventRecord(k.copied, c->copy_stream));
+		VGB_CUDA(c, cudaStreamWaitEvent(c->stream, k.copied, 0));
+		auto in_pinned = [&](const Chunk &q) { return q.h_pinned && host_chunk >= q.h_pinned && host_chunk < q.h_pinned + c->max_chunk_bytes; };
+		if (!in_pinned(k) && !in_pinned(c->chunk[slot ^ 1]))
+			VGB_CUDA(c, cudaEventSynchronize(k.copied));   // caller's own memory: safe to reuse on return
+	}
+	const int rc = process_text(c, k, nbytes, first_read_id, 0, 0, 0);
+	if (device_chunk) k.d_text = own_text;
+	return rc;
+}
+
+// BGZF chunk: compressed members over PCIe, inflated on the device straight into the chunk's text buffer
+static int submit_bgzf(vgb_ctx *c, const uint8_t *comp, uint64_t comp_bytes, const vgb_bgzf_member *mem, uint32_t n_mem, uint64_t ov, int last)
+{
+	if (!c->have_index) return set_err(c, VGB_E_ARG, "vgb_index_upload has not been called");
+	if (comp_bytes > c->max_chunk_bytes) return set_err(c, VGB_E_ARG, "compressed chunk of %llu bytes exceeds max_chunk_bytes", (unsigned long long)comp_bytes);
+	if (n_mem == 0) return VGB_OK;
+	cudaSetDevice(c->device);
+	const int slot = c->next_slot;
+	c->next_slot ^= 1;
+	Chunk &k = c->chunk[slot];
+	collect_times(c, slot);
+	if (!k.d_comp) VGB_CUDA(c, cudaMalloc((void **)&k.d_comp, c->max_chunk_bytes + 64));
+	if (k.blk_cap < n_mem) {
+		const uint32_t cap = std::max<uint32_t>(n_mem, 2 * k.blk_cap + 1024);
+		if (k.d_blk) cudaFree(k.d_blk);
+		if (k.h_blk) cudaFreeHost(k.h_blk);
+		k.d_blk = nullptr; k.h_blk = nullptr; k.blk_cap = 0;
+		VGB_CUDA(c, cudaMalloc((void **)&k.d_blk, (size_t)cap * sizeof(BgzfBlock)));
+		VGB_CUDA(c, cudaMallocHost((void **)&k.h_blk, (size_t)cap * sizeof(BgzfBlock)));
+		k.blk_cap = cap;
+	}
+	uint64_t out = 0;
+	for (uint32_t i = 0; i < n_mem; i++) {
+		if ((uint64_t)mem[i].comp_offset + mem[i].comp_len > comp_bytes || mem[i].out_len > 65536)
+			return set_err(c, VGB_E_ARG, "BGZF member %u lies outside the chunk or claims more than 64 KiB", i);
+		k.h_blk[i] = BgzfBlock{ mem[i].comp_offset, mem[i].comp_len, (uint32_t)out, mem[i].out_len };
+		out += mem[i].out_len;
+	}
+	if (out > c->max_chunk_bytes) return set_err(c, VGB_E_ARG, "chunk inflates to %llu bytes, more than max_chunk_bytes", (unsigned long long)out);
+	if (ov > out) return set_err(c, VGB_E_ARG, "overlap larger than the chunk");
+	VGB_CUDA(c, cudaMemcpyAsync(k.d_comp, comp, comp_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+	VGB_CUDA(c, cudaMemcpyAsync(k.d_blk, k.h_blk, (size_t)n_mem * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->copy_stream));
+	VGB_CUDA(c, cudaEventRecord(k.copied, c->copy_stream));
+	VGB_CUDA(c, cudaStreamWaitEvent(c->stream, k.copied, 0));
+	const char *hc = (const char *)comp;
+	auto in_pinned = [&](const Chunk &q) { return q.h_pinned && hc >= q.h_pinned && hc < q.h_pinned + c->max_chunk_bytes; };
+	if (!in_pinned(k) && !in_pinned(c->chunk[slot ^ 1])) VGB_CUDA(c, cudaEventSynchronize(k.copied));
+	if (out == 0) { cudaEventRecord(k.done, c->stream); k.busy = true; return VGB_OK; }
+	int rc = bgzf_inflate(c, k, k.d_comp, k.d_blk, n_mem, c->stream);
+	if (rc != VGB_OK) return rc;
+	return process_text(c, k, out, 0, 1, ov, last);
 }
 
 }  // namespace vgb
@@ -269,6 +318,12 @@ int vgb_submit_fastq_device(vgb_ctx *c, const char *device_chunk, uint64_t nbyte
 {
 	if (!device_chunk && nbytes) return c ? set_err(c, VGB_E_ARG, "null chunk") : VGB_E_ARG;
 	return submit_common(c, nullptr, device_chunk, nbytes, first_read_id);
+}
+
+int vgb_submit_bgzf(vgb_ctx *c, const void *comp, uint64_t comp_bytes, const vgb_bgzf_member *members, uint32_t n_members, uint64_t overlap_bytes, int last_chunk)
+{
+	if (!c || (n_members && (!comp || !members))) return c ? set_err(c, VGB_E_ARG, "null argument") : VGB_E_ARG;
+	return submit_bgzf(c, (const uint8_t *)comp, comp_bytes, members, n_members, overlap_bytes, last_chunk);
 }
 
 int vgb_sync(vgb_ctx *c)
@@ -288,6 +343,7 @@ int vgb_sync(vgb_ctx *c)
 	DevStats st;
 	VGB_CUDA(c, vgb::copy_sync(c, &st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
 	c->sticky_format |= bits;
+	if (c->sticky_format & 8) return set_err(c, VGB_E_FORMAT, "BGZF input: a gzip member is corrupt or does not inflate to the size its trailer states");
 	if (c->sticky_format || st.bad_records)
 		return set_err(c, VGB_E_FORMAT, "FASTQ input violates the contract:%s%s%s (%llu bad records)",
 		               (c->sticky_format & 1) ? " truncated record (line count not a multiple of 4);" : "",

@@ -4,8 +4,10 @@
 // HBM; one single-pass kernel finds every line start (newline masks per 64 KiB tile, decoupled look-back for the
 // running line number, scatter from registers), so the per-read kernel can address record r as lines 4r .. 4r+3
 // without any host parsing.  Streaming, 128-bit loads, bounded by HBM bandwidth (the text is read ONCE + 4 B written per line).
+#include <algorithm>
 #include <cstdlib>
 
+#include "vgb_inflate.cuh"
 #include "vgb_internal.h"
 
 namespace vgb {
@@ -102,19 +104,41 @@ __global__ void __launch_bounds__(FQ_T) k_fq_index(const char *text, uint64_t n,
 	}
 }
 
-// meta: [0] n_lines [1] n_reads [2] work counter [3] format error bits
-__global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_nl, uint32_t *meta, uint32_t *line_start, uint64_t line_cap)
+// meta: [0] n_lines [1] n_reads [2] work counter [3] format error bits [11] first line of the chunk's own records
+// window (BGZF chunks, see bgzf_submit): the text starts with `ov` bytes that belong to the previous chunk (its last blocks,
+// inflated again so that a record cut by the chunk boundary is whole here).  Lines are phased by the first '@' line whose second
+// next line starts with '+'; the chunk owns the complete records that END behind byte ov; what is left behind the last complete
+// record belongs to the next chunk (or is a truncated record when this is the last one).
+__global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_nl, uint32_t *meta, uint32_t *line_start, uint64_t line_cap,
+                            int window, uint64_t ov, int last)
 {
 	uint32_t lines = *total_nl;
-	uint32_t err = 0;
-	const bool open_tail = n > 0 && text[n - 1] != '\n';   // last line without '\n': treated as terminated
+	uint32_t err = 0, first = 0, reads = 0;
+	const bool open_tail = n > 0 && text[n - 1] != '\n';   // last line without '\n': treated as terminated (end of the input only)
 	if ((uint64_t)lines + 2 > line_cap) { err |= 4; lines = 0; }
 	else {
 		line_start[0] = 0;
-		if (open_tail) { line_start[lines + 1] = (uint32_t)(n + 1); lines += 1; }
+		if (open_tail && (!window || last)) { line_start[lines + 1] = (uint32_t)(n + 1); lines += 1; }
 	}
-	if (lines % 4) err |= 1;                               // truncated record (the reference would reuse stale buffers)
-	meta[0] = lines; meta[1] = lines / 4; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0; meta[9] = 0; meta[10] = 0;
+	if (!window) {
+		if (lines % 4) err |= 1;                           // truncated record (the reference would reuse stale buffers)
+		reads = lines / 4;
+	} else if (lines >= 4 || (last && lines)) {
+		uint32_t p = 0;
+		bool found = ov == 0;                              // the first chunk starts at the beginning of the input
+		for (; !found && p + 2 < lines && p < 16; p++)
+			if (text[line_start[p]] == '@' && text[line_start[p + 2]] == '+') { found = true; break; }
+		if (!found) err |= 1;
+		else {
+			const uint32_t n_rec = (lines - p) / 4;
+			uint32_t j0 = 0;
+			while (j0 < n_rec && (uint64_t)line_start[p + 4 * (j0 + 1)] <= ov) j0++;    // records that end inside the overlap: the previous chunk's
+			first = p + 4 * j0;
+			reads = n_rec - j0;
+			if (last && (lines - p) % 4) err |= 1;
+		}
+	}
+	meta[0] = lines; meta[1] = reads; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0; meta[9] = 0; meta[10] = 0; meta[11] = first;
 	meta[5] |= err;                                        // sticky until vgb_reset_counts (the slot is reused by later chunks)
 }
 
@@ -131,7 +155,7 @@ static cudaError_t launch_fq_index(Chunk &ck, uint64_t nbytes, uint64_t line_cap
 	return cudaSuccess;
 }
 
-int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
+int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st, int window, uint64_t ov, int last)
 {
 	const uint64_t line_cap = c->max_chunk_bytes / 2 + 16;
 	const int variant = getenv("VGB_FQ_VARIANT") ? atoi(getenv("VGB_FQ_VARIANT")) : 0;   // tuning aid (tools/perf_sweep.py)
@@ -144,8 +168,39 @@ int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st)
 	default: e = launch_fq_index<256, 256>(ck, nbytes, line_cap, st); break;
 	}
 	VGB_CUDA(c, e);
-	k_fq_finish<<<1, 1, 0, st>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap);
+	k_fq_finish<<<1, 1, 0, st>>>(ck.d_text, nbytes, ck.d_meta + 4, ck.d_meta, ck.d_line_start, line_cap, window, ov, last);
 	c->launches += 2;
+	VGB_CUDA(c, cudaGetLastError());
+	return VGB_OK;
+}
+
+// ---- BGZF: the gzip members of a chunk inflated on the device, one warp per member (vgb_inflate.cuh) ----
+constexpr int INF_WARPS = 8;
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t *comp, const BgzfBlock *blk, uint32_t n_blk, uint8_t *out, uint32_t *meta,
+                                                                 uint32_t *next_block)
+{
+	__shared__ InflateTables tables[INF_WARPS];
+	InflateTables &t = tables[threadIdx.x >> 5];
+	const uint32_t lane = threadIdx.x & 31;
+	for (;;) {
+		uint32_t b = 0;
+		if (lane == 0) b = atomicAdd(next_block, 1u);
+		b = __shfl_sync(0xffffffffu, b, 0);
+		if (b >= n_blk) break;
+		const BgzfBlock k = blk[b];
+		uint32_t got = 0;
+		const int rc = inflate_block(comp + k.comp_off, k.comp_len, out + k.out_off, k.out_len, t, &got);
+		if (lane == 0 && (rc != INF_OK || got != k.out_len)) atomicOr(&meta[5], 8u);   // corrupt member: sticky, reported by vgb_sync
+		__syncwarp();
+	}
+}
+
+int bgzf_inflate(vgb_ctx *c, Chunk &ck, const uint8_t *d_comp, const BgzfBlock *d_blk, uint32_t n_blk, cudaStream_t st)
+{
+	VGB_CUDA(c, cudaMemsetAsync(ck.d_meta + 12, 0, sizeof(uint32_t), st));                // member counter
+	const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * 6, (n_blk + INF_WARPS - 1) / INF_WARPS);
+	k_inflate_bgzf<<<grid ? grid : 1, INF_WARPS * 32, 0, st>>>(d_comp, d_blk, n_blk, reinterpret_cast<uint8_t *>(ck.d_text), ck.d_meta, ck.d_meta + 12);
+	c->launches++;
 	VGB_CUDA(c, cudaGetLastError());
 	return VGB_OK;
 }

@@ -43,7 +43,7 @@ struct GenoArgs {
 	DevIndex ix;
 	const char *text;
 	const uint32_t *line_start;
-	uint32_t *meta;               // [1] n_reads [2] work counter [3] error bits
+	uint32_t *meta;               // [1] n_reads [2] work counter [3] error bits [11] first line of the chunk's own records
 	DevStats *stats;
 	vgb_read_result *trace;       // nullptr unless VGB_CFG_TRACE
 	Event *spill;                 // [grid warps][EV_CAP - EV_SMEM]
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 			const uint32_t rr = a.list ? __ldg(a.list + ri) : ri;
 			const uint32_t r = rr & 0x7FFFFFFFu;
 			// ---- record framing: lines 4r .. 4r+3 (src/qv.cc:760-779) ----
-			uint32_t lsv = lane < 5 ? __ldg(a.line_start + 4ull * r + lane) : 0;
+			uint32_t lsv = lane < 5 ? __ldg(a.line_start + a.meta[11] + 4ull * r + lane) : 0;   // meta[11]: first line of the chunk's own records (BGZF window)
 			const uint32_t id_s = __shfl_sync(0xffffffffu, lsv, 0);
 			const uint32_t seq_s = __shfl_sync(0xffffffffu, lsv, 1);
 			const uint32_t sep_s = __shfl_sync(0xffffffffu, lsv, 2);

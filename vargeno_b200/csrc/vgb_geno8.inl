@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 	// list mode (the 8-lane instantiation behind the 4-lane one): only the reads the 4-lane kernel handed over (5..8 k-mers)
 	const uint32_t n_reads = a.klist ? a.meta[9] : a.meta[1];
 	uint32_t *work = a.meta + (a.klist ? 10 : 2);
+	const uint32_t *ls0 = a.line_start + a.meta[11];      // first line of the chunk's own records (non-zero only for BGZF windows)
 	const uint32_t FULL = 0xffffffffu;
 #define OSHFL(v, src) __shfl_sync(FULL, (v), ob | (src))
 #define OBALLOT(p) ((__ballot_sync(FULL, (p)) >> ob) & GM)
@@ -183,8 +184,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 			// ---- record framing (src/qv.cc:760-779): line starts 4r .. 4r+4 ----
 			uint32_t lsv = 0, lsn = 0;
-			if (have && ol < 4) lsv = __ldg(a.line_start + 4ull * r + ol);
-			if (have && ol == 0) lsn = __ldg(a.line_start + 4ull * r + 4);
+			if (have && ol < 4) lsv = __ldg(ls0 + 4ull * r + ol);
+			if (have && ol == 0) lsn = __ldg(ls0 + 4ull * r + 4);
 			const uint32_t id_s = OSHFL(lsv, 0), seq_s = OSHFL(lsv, 1), sep_s = OSHFL(lsv, 2), qual_s = OSHFL(lsv, 3), next_s = OSHFL(lsn, 0);
 			const uint32_t L = sep_s - 1 - seq_s;
 			const uint32_t qlen = next_s - 1 - qual_s;

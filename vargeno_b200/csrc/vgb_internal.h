@@ -17,6 +17,8 @@ struct DevStats {   // device-resident counters, one cache line apart from nothi
 	    lowq_kmers, events, pileup_incr, big_kmers, bad_records, overflow_reads, freq_wrap_reads, first_error;
 };
 
+struct BgzfBlock { uint32_t comp_off, comp_len, out_off, out_len; };   // one gzip member of a chunk: DEFLATE payload in the compressed buffer -> place in the text
+
 struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i+1 overlaps the kernels of chunk i)
 	char *d_text = nullptr;           // device copy of the text (owned unless external)
 	char *h_pinned = nullptr;         // pinned staging buffer handed out by vgb_pinned_buffer
@@ -24,7 +26,10 @@ struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i
 	uint32_t *d_blk_counts = nullptr; // newline count per 4 KiB tile, then its exclusive scan
 	uint32_t *d_defer = nullptr;      // read indices the group kernels hand to the warp-per-read kernel
 	uint32_t *d_defer2 = nullptr;     // read indices the 4-lane kernel hands to the 8-lane kernel
-	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter
+	uint8_t *d_comp = nullptr;        // BGZF: compressed members of the chunk (allocated at the first vgb_submit_bgzf)
+	BgzfBlock *d_blk = nullptr, *h_blk = nullptr;   // their table, device copy and pinned staging
+	uint32_t blk_cap = 0;
+	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter [11] first line of the chunk's own records [12] BGZF member counter
 	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, g0 = nullptr;
 	bool busy = false;
 };
@@ -120,7 +125,8 @@ int dev_alloc(vgb_ctx *c, T **p, uint64_t count, bool own = true)
 // vgb_index.cu
 int index_upload(vgb_ctx *c, const vgb_index_view *v);
 // vgb_fastq.cu
-int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st);
+int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st, int window = 0, uint64_t ov = 0, int last = 0);
+int bgzf_inflate(vgb_ctx *c, Chunk &ck, const uint8_t *d_comp, const BgzfBlock *d_blk, uint32_t n_blk, cudaStream_t st);
 // vgb_geno.cu
 int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id);
 int geno_prepare(vgb_ctx *c);

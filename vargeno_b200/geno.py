@@ -139,6 +139,23 @@ class Genotyper:
         self._ck(self.L.vgb_pinned_buffer(self.h, slot, C.byref(p), C.byref(cap)))
         self._ck(self.L.vgb_submit_fastq(self.h, p, nbytes, first_read_id))
 
+    def submit_bgzf(self, comp: np.ndarray, members: np.ndarray, overlap_bytes: int, last_chunk: bool) -> None:
+        """One vgb_submit_bgzf call: `comp` = gzip members back to back (uint8), `members` = uint32[n][3] rows of
+        (DEFLATE payload offset in comp, payload length, ISIZE); see tools/bgzf.chunk_arrays."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        members = np.ascontiguousarray(members, dtype="<u4")
+        self._ck(self.L.vgb_submit_bgzf(self.h, _lib.ptr(comp), comp.size, _lib.ptr(members), members.shape[0], overlap_bytes, 1 if last_chunk else 0))
+
+    def submit_bgzf_file(self, buf: bytes, own_out: int) -> int:
+        """A whole BGZF file image through vgb_submit_bgzf in chunks of about `own_out` inflated bytes, planned the way the C++ host
+        plans them (overlap of >= 8 KiB of text from the previous chunk).  Returns the number of chunks."""
+        from .tools import bgzf
+        mem, plan = bgzf.plan_chunks(bgzf.scan(buf), own_out)
+        for k, (o0, i0, i1, ov) in enumerate(plan):
+            comp, tab = bgzf.chunk_arrays(buf, mem, o0, i1)
+            self.submit_bgzf(comp, tab, ov, k + 1 == len(plan))
+        return len(plan)
+
     def submit_device(self, dptr: int, nbytes: int, first_read_id: int = 0) -> None:
         self._ck(self.L.vgb_submit_fastq_device(self.h, C.c_void_p(dptr), nbytes, first_read_id))
 
