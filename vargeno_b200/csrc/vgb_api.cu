@@ -197,7 +197,7 @@ static void collect_times(vgb_ctx *c, int slot)
 // the text of the chunk is (or will be, in stream order) in k.d_text: record framing, then the per-read kernels
 static int process_text(vgb_ctx *c, Chunk &k, uint64_t nbytes, uint64_t first_read_id, int window, uint64_t ov, int last)
 {
-	VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));
+	if (!window) VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));      // BGZF chunks: recorded in front of the inflate kernel, which counts as parsing
 	int rc = fastq_index_lines(c, k, nbytes, c->stream, window, ov, last);
 	if (rc == VGB_OK) {
 		VGB_CUDA(c, cudaEventRecord(k.t1, c->stream));
@@ -299,6 +299,7 @@ static int submit_bgzf(vgb_ctx *c, const uint8_t *comp, uint64_t comp_bytes, con
 	auto in_pinned = [&](const Chunk &q) { return q.h_pinned && hc >= q.h_pinned && hc < q.h_pinned + c->max_chunk_bytes; };
 	if (!in_pinned(k) && !in_pinned(c->chunk[slot ^ 1])) VGB_CUDA(c, cudaEventSynchronize(k.copied));
 	if (out == 0) { cudaEventRecord(k.done, c->stream); k.busy = true; return VGB_OK; }
+	VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));
 	int rc = bgzf_inflate(c, k, k.d_comp, k.d_blk, n_mem, c->stream);
 	if (rc != VGB_OK) return rc;
 	return process_text(c, k, out, 0, 1, ov, last);

@@ -61,16 +61,27 @@ struct InflateBits {                    // LSB-first bit reader over [in, in + n
 	bool over;                          // ran past the end of the input
 };
 
+// 32 more bits whenever at most 32 are left: one unaligned word per refill (two aligned loads on the device) instead of a byte
+// at a time -- the refill sits on the critical path of every symbol
 INF_HD void inf_refill(InflateBits &b)
 {
-	while (b.bc <= 56) {
-		uint64_t byte = 0;
-		if (b.ip < b.n) byte = b.in[b.ip];
-		else if (b.ip >= b.n + 8) { b.over = true; }       // a few zero bytes behind the end are legal look-ahead, more is not
-		b.ip++;
-		b.bb |= byte << b.bc;
-		b.bc += 8;
+	if (b.bc > 32) return;
+	uint32_t w = 0;
+	if (b.ip + 4 <= b.n) {
+#ifdef __CUDACC__
+		const uintptr_t a = reinterpret_cast<uintptr_t>(b.in + b.ip);
+		const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+		w = __funnelshift_r(wp[0], wp[1], (uint32_t)(a & 3) * 8);      // the bytes in front of / behind the payload are header / trailer bytes of the same buffer
+#else
+		for (int i = 0; i < 4; i++) w |= (uint32_t)b.in[b.ip + i] << (8 * i);
+#endif
+	} else {
+		for (int i = 0; i < 4; i++) if (b.ip + i < b.n) w |= (uint32_t)b.in[b.ip + i] << (8 * i);
+		if (b.ip >= b.n + 8) b.over = true;                 // a few zero bytes behind the end are legal look-ahead, more is not
 	}
+	b.ip += 4;
+	b.bb |= (uint64_t)w << b.bc;
+	b.bc += 32;
 }
 INF_HD uint32_t inf_take(InflateBits &b, uint32_t k)        // k <= 32
 {
@@ -140,14 +151,14 @@ INF_HD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym
 
 INF_HD int inf_decode_lit(InflateBits &b, const InflateTables &t)
 {
-	if (b.bc < 15) inf_refill(b);
+	if (b.bc < 32) inf_refill(b);
 	const uint16_t e = t.lit[b.bb & ((1u << INF_LIT_BITS) - 1)];
 	if (e) { b.bb >>= (e & 15); b.bc -= (e & 15); return e >> 4; }
 	return inf_slow(b, t.lcount, t.lsym);
 }
 INF_HD int inf_decode_dst(InflateBits &b, const InflateTables &t)
 {
-	if (b.bc < 15) inf_refill(b);
+	if (b.bc < 32) inf_refill(b);
 	const uint16_t e = t.dst[b.bb & ((1u << INF_DST_BITS) - 1)];
 	if (e) { b.bb >>= (e & 15); b.bc -= (e & 15); return e >> 4; }
 	return inf_slow(b, t.dcount, t.dsym);
@@ -268,7 +279,8 @@ INF_HD int inflate_block(const uint8_t *in, uint64_t in_len, uint8_t *out, uint3
 				if (err) { status = (int)err; break; }
 				if (eob) break;
 				// the match: every byte comes from the part of the output that is already complete (i mod distance)
-				for (uint32_t i = lane; i < mlen; i += INF_LANES) out[pos + i] = INF_LOAD_OUT(out + pos - mdist + (i % mdist));
+				if (mdist >= mlen) { for (uint32_t i = lane; i < mlen; i += INF_LANES) out[pos + i] = INF_LOAD_OUT(out + pos - mdist + i); }
+				else { for (uint32_t i = lane; i < mlen; i += INF_LANES) out[pos + i] = INF_LOAD_OUT(out + pos - mdist + (i % mdist)); }
 				pos += mlen;
 				INF_SYNC();
 			}

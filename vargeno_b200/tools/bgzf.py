@@ -80,3 +80,35 @@ def chunk_arrays(buf: bytes, mem, o0: int, i1: int):
         tab.append((at + poff, size - poff - 8, isize))
         at += size
     return np.frombuffer(b"".join(parts), dtype=np.uint8), np.array(tab, dtype="<u4").reshape(-1, 3)
+
+
+def _span(args):
+    path, start, n, block, level = args
+    with open(path, "rb") as f:
+        f.seek(start)
+        data = f.read(n)
+    return b"".join(member(data[a:a + block], level) for a in range(0, len(data), block))
+
+
+def compress_file(src: str, dst: str, procs: int = 8, block: int = 65280, level: int = 1, span_blocks: int = 512) -> None:
+    """src -> BGZF dst with `procs` worker processes (what `bgzip -@ N` does); spans are whole numbers of members."""
+    import multiprocessing as mp
+    import os
+    size = os.path.getsize(src)
+    span = block * span_blocks
+    jobs = [(src, a, min(span, size - a), block, level) for a in range(0, size, span)]
+    with mp.Pool(procs) as pool, open(dst, "wb") as out:
+        for piece in pool.imap(_span, jobs, chunksize=1):
+            out.write(piece)
+        out.write(EOF_MEMBER)
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="write a file as BGZF (multi-process)")
+    ap.add_argument("src")
+    ap.add_argument("dst")
+    ap.add_argument("--procs", type=int, default=8)
+    ap.add_argument("--level", type=int, default=1)
+    a = ap.parse_args()
+    compress_file(a.src, a.dst, a.procs, level=a.level)

@@ -45,6 +45,7 @@ class DeviceWorkload:
     host_genome: Optional[np.ndarray] = None
     host_index: Optional[ib.Index] = None
     host_haps: Optional[Tuple[np.ndarray, np.ndarray]] = None
+    host_snps: Optional[synth.SnpSet] = None
 
 
 def repeat_ops(total: int, seed: int, frac: float) -> List[Tuple[int, int, int]]:
@@ -151,7 +152,7 @@ def build(g: "geno.Genotyper", contigs: Sequence[Tuple[str, int]], n_snps: int, 
     if verbose:
         print("device workload %s: %s %s" % (name, counts, {k: round(v, 2) for k, v in t.items()}), flush=True)
     return DeviceWorkload(name, names, starts, lens, total, h0d, h1d, read_len, seed, int(dict_ok.sum()), counts, t,
-                          cat if keep_host else None, host_index, (h0, h1) if keep_host else None)
+                          cat if keep_host else None, host_index, (h0, h1) if keep_host else None, snps if keep_host else None)
 
 
 def build_s1(g: "geno.Genotyper", scale: float = 1.0, seed: int = 7, keep_host: bool = False, verbose: bool = False) -> DeviceWorkload:
