@@ -4,6 +4,6 @@
 
 extern "C" int vgb_host_inflate(const unsigned char *in, unsigned long long in_len, unsigned char *out, unsigned out_cap, unsigned *out_len)
 {
-	static vgb::InflateTables t;
+	static vgb::InflateWarp t;
 	return vgb::inflate_block(in, in_len, out, out_cap, t, out_len);
 }

@@ -44,6 +44,10 @@ def _fastq(n, seed):
     return "".join(recs).encode()
 
 
+def _rnd(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
 CASES = {
     "empty": b"",
     "one_byte": b"A",
@@ -53,6 +57,11 @@ CASES = {
     "random": np.random.default_rng(2).integers(0, 256, 65536, dtype=np.uint8).tobytes(),     # incompressible: stored blocks
     "skewed": bytes(np.minimum(255, np.random.default_rng(3).geometric(0.02, 60000)).astype(np.uint8)),   # long codes (> 10 bits)
     "text": (b"the quick brown fox jumps over the lazy dog. " * 1400)[:65000],
+    # matches that reach further back than the decoder's 8 KiB ring (read back from the flushed output), into a stored block that
+    # is still in the ring, and into one that is not
+    "far_repeat": _rnd(20000, 4) * 3,
+    "stored_then_near": _rnd(3000, 5) * 4 + b"ACGT" * 500 + _rnd(3000, 5),
+    "stored_then_far": _rnd(30000, 6) + _rnd(30000, 6)[:12000] + b"N" * 700 + _rnd(30000, 6)[5000:9000],
 }
 
 
@@ -109,3 +118,16 @@ def test_errors_are_reported(lib):
         junk = rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8).tobytes()
         rc, out = _inflate(lib, junk, 4096)
         assert len(out) <= 4096
+
+
+@pytest.mark.parametrize("n_stored", [100, 3000, 7900, 20000, 65535])
+def test_matches_into_a_stored_block(lib, n_stored):
+    """stored block + a compressed block whose matches point into it (written by zlib against a preset dictionary): near ones
+    come out of the decoder's ring, far ones out of the text that is already flushed."""
+    first = _rnd(n_stored, 7)
+    second = first[-5000:] + b"ACGT" * 300 + first[:4000] + first[n_stored // 2:n_stored // 2 + 300]
+    c = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_DEFAULT_STRATEGY, first[-32768:])
+    tail = c.compress(second) + c.flush()
+    stored = bytes([0]) + len(first).to_bytes(2, "little") + (len(first) ^ 0xFFFF).to_bytes(2, "little") + first
+    rc, out = _inflate(lib, stored + tail, len(first) + len(second))
+    assert rc == 0 and out == first + second

@@ -84,6 +84,7 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 		CK(cudaMalloc((void **)&k.d_blk_counts, (2 * nblk + 64) * 4));
 		CK(cudaMalloc((void **)&k.d_defer, (c->max_chunk_bytes / 8 + 16) * 4));
 		CK(cudaMalloc((void **)&k.d_defer2, (c->max_chunk_bytes / 8 + 16) * 4));
+		CK(cudaMalloc((void **)&k.d_defer3, (c->max_chunk_bytes / 8 + 16) * 4));
 		CK(cudaMalloc((void **)&k.d_meta, 64));
 		CK(vgb::memset_sync(c, k.d_meta, 0, 64));
 		CK(cudaEventCreateWithFlags(&k.copied, cudaEventDisableTiming));
@@ -123,7 +124,7 @@ void vgb_ctx_destroy(vgb_ctx *c)
 	for (int i = 0; i < c->n_owned; i++) cudaFree(c->owned[i]);
 	for (int s = 0; s < 2; s++) {
 		Chunk &k = c->chunk[s];
-		cudaFree(k.d_text); cudaFree(k.d_line_start); cudaFree(k.d_blk_counts); cudaFree(k.d_meta); cudaFree(k.d_defer); cudaFree(k.d_defer2);
+		cudaFree(k.d_text); cudaFree(k.d_line_start); cudaFree(k.d_blk_counts); cudaFree(k.d_meta); cudaFree(k.d_defer); cudaFree(k.d_defer2); cudaFree(k.d_defer3);
 		if (k.h_pinned) cudaFreeHost(k.h_pinned);
 		if (k.copied) cudaEventDestroy(k.copied);
 		if (k.done) cudaEventDestroy(k.done);

@@ -138,7 +138,7 @@ __global__ void k_fq_finish(const char *text, uint64_t n, const uint32_t *total_
 			if (last && (lines - p) % 4) err |= 1;
 		}
 	}
-	meta[0] = lines; meta[1] = reads; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0; meta[9] = 0; meta[10] = 0; meta[11] = first;
+	meta[0] = lines; meta[1] = reads; meta[2] = 0; meta[3] = err; meta[6] = 0; meta[7] = 0; meta[9] = 0; meta[10] = 0; meta[11] = first; meta[13] = 0; meta[14] = 0;
 	meta[5] |= err;                                        // sticky until vgb_reset_counts (the slot is reused by later chunks)
 }
 
@@ -175,12 +175,14 @@ int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st, i
 }
 
 // ---- BGZF: the gzip members of a chunk inflated on the device, one warp per member (vgb_inflate.cuh) ----
-constexpr int INF_WARPS = 8;
+// 6 warps of 12.1 KiB (ring + tables) per CTA, three CTAs per SM: 18 members in flight per SM.  Members are claimed one at a time
+// through a counter: their cost varies with what they hold.
+constexpr int INF_WARPS = 6;
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t *comp, const BgzfBlock *blk, uint32_t n_blk, uint8_t *out, uint32_t *meta,
                                                                  uint32_t *next_block)
 {
-	__shared__ InflateTables tables[INF_WARPS];
-	InflateTables &t = tables[threadIdx.x >> 5];
+	extern __shared__ __align__(16) unsigned char inf_smem[];
+	InflateWarp &ws = reinterpret_cast<InflateWarp *>(inf_smem)[threadIdx.x >> 5];
 	const uint32_t lane = threadIdx.x & 31;
 	for (;;) {
 		uint32_t b = 0;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t *
 		if (b >= n_blk) break;
 		const BgzfBlock k = blk[b];
 		uint32_t got = 0;
-		const int rc = inflate_block(comp + k.comp_off, k.comp_len, out + k.out_off, k.out_len, t, &got);
+		const int rc = inflate_block(comp + k.comp_off, k.comp_len, out + k.out_off, k.out_len, ws, &got);
 		if (lane == 0 && (rc != INF_OK || got != k.out_len)) atomicOr(&meta[5], 8u);   // corrupt member: sticky, reported by vgb_sync
 		__syncwarp();
 	}
@@ -197,9 +199,17 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t *
 
 int bgzf_inflate(vgb_ctx *c, Chunk &ck, const uint8_t *d_comp, const BgzfBlock *d_blk, uint32_t n_blk, cudaStream_t st)
 {
+	const size_t smem = sizeof(InflateWarp) * INF_WARPS;
+	if (!c->inflate_ready) {
+		int occ = 0;
+		VGB_CUDA(c, cudaFuncSetAttribute(k_inflate_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_bgzf, INF_WARPS * 32, smem));
+		c->inflate_grid = (uint32_t)(c->sm_count * (occ > 0 ? occ : 1));
+		c->inflate_ready = true;
+	}
 	VGB_CUDA(c, cudaMemsetAsync(ck.d_meta + 12, 0, sizeof(uint32_t), st));                // member counter
-	const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * 6, (n_blk + INF_WARPS - 1) / INF_WARPS);
-	k_inflate_bgzf<<<grid ? grid : 1, INF_WARPS * 32, 0, st>>>(d_comp, d_blk, n_blk, reinterpret_cast<uint8_t *>(ck.d_text), ck.d_meta, ck.d_meta + 12);
+	const unsigned grid = (unsigned)std::min<uint64_t>(c->inflate_grid, (n_blk + INF_WARPS - 1) / INF_WARPS);
+	k_inflate_bgzf<<<grid ? grid : 1, INF_WARPS * 32, smem, st>>>(d_comp, d_blk, n_blk, reinterpret_cast<uint8_t *>(ck.d_text), ck.d_meta, ck.d_meta + 12);
 	c->launches++;
 	VGB_CUDA(c, cudaGetLastError());
 	return VGB_OK;

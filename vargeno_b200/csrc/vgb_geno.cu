@@ -47,10 +47,11 @@ struct GenoArgs {
 	DevStats *stats;
 	vgb_read_result *trace;       // nullptr unless VGB_CFG_TRACE
 	Event *spill;                 // [grid warps][EV_CAP - EV_SMEM]
-	const uint32_t *list;         // warp kernel: nullptr = every read of the chunk, else the deferred reads (count in meta[6])
-	uint32_t *defer;              // group kernels: where read indices for the warp kernel go (bit 31: start at the retry pass)
-	const uint32_t *klist;        // 8-lane kernel behind the 4-lane one: the reads it was handed (count in meta[9]); nullptr = whole chunk
-	uint32_t *kdefer;             // 4-lane kernel: reads with 5..8 k-mers, for the 8-lane kernel
+	const uint32_t *list;         // warp kernel: nullptr = every read of the chunk, else the deferred reads (count in meta[in_cnt])
+	uint32_t *defer;              // group kernels: where reads go that need the next kernel (count in meta[defer_cnt]; bit 31: start at the retry pass)
+	const uint32_t *klist;        // group kernels behind the 4-lane one: the reads they were handed (count in meta[in_cnt]); nullptr = whole chunk
+	uint32_t *kdefer;             // 4-lane kernel: reads with 5..8 k-mers, for the 8-lane kernel (count in meta[9])
+	uint32_t in_cnt, defer_cnt;   // meta slots: in_cnt = length of list / klist (in_cnt + 1: its work counter), defer_cnt = length of defer
 };
 
 struct LaneStats {
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 	Event *spill = a.spill + (uint64_t)gwarp * (EV_CAP - EV_SMEM);
 	const DevIndex &ix = a.ix;
 	// list mode: only the reads the 8-lane kernel deferred (more than 8 k-mers, or more hit contexts than its shared memory holds)
-	const uint32_t n_reads = a.list ? a.meta[6] : a.meta[1];
-	uint32_t *work = a.meta + (a.list ? 7 : 2);
+	const uint32_t n_reads = a.list ? a.meta[a.in_cnt] : a.meta[1];
+	uint32_t *work = a.meta + (a.list ? a.in_cnt + 1 : 2);
 	LaneStats st;
 	uint32_t w_reads = 0, w_skipped = 0, w_passes = 0, w_placed = 0, w_bad = 0, w_overflow = 0, w_wrap = 0;
 
@@ -494,15 +495,19 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 #include "vgb_geno8.inl"
 
 typedef void (*geno_kernel_t)(const GenoArgs);
-static size_t grp_smem_bytes(int G) { const size_t R = 32 / G; return sizeof(OctSmem) * GW * R + GW * 16 * sizeof(uint32_t) + (G == 4 ? sizeof(Pend<4>) : sizeof(Pend<8>)) * GW * 2 * R; }
+static size_t grp_smem_bytes(int G, bool wide = false)
+{
+	const size_t R = 32 / G;
+	return (wide ? sizeof(OctSmem<EV_WIDE>) : sizeof(OctSmem<EV_GROUP>)) * GW * R + GW * 16 * sizeof(uint32_t) + (G == 4 ? sizeof(Pend<4>) : sizeof(Pend<8>)) * GW * 2 * R;
+}
 
 template <int G>
 static void pick_group_kernels(int minb, geno_kernel_t &k, geno_kernel_t &kt)
 {
-	if (minb >= 6) { k = k_geno8<6, false, G>; kt = k_geno8<6, true, G>; }
-	else if (minb == 5) { k = k_geno8<5, false, G>; kt = k_geno8<5, true, G>; }
-	else if (minb == 3) { k = k_geno8<3, false, G>; kt = k_geno8<3, true, G>; }
-	else { k = k_geno8<4, false, G>; kt = k_geno8<4, true, G>; }
+	if (minb >= 6) { k = k_geno8<6, false, G, EV_GROUP>; kt = k_geno8<6, true, G, EV_GROUP>; }
+	else if (minb == 5) { k = k_geno8<5, false, G, EV_GROUP>; kt = k_geno8<5, true, G, EV_GROUP>; }
+	else if (minb == 3) { k = k_geno8<3, false, G, EV_GROUP>; kt = k_geno8<3, true, G, EV_GROUP>; }
+	else { k = k_geno8<4, false, G, EV_GROUP>; kt = k_geno8<4, true, G, EV_GROUP>; }
 }
 
 int geno_prepare(vgb_ctx *c)
@@ -518,20 +523,23 @@ int geno_prepare(vgb_ctx *c)
 	const bool warp_only = kk && !strcmp(kk, "warp");
 	c->use_quad = !(kk && !strcmp(kk, "oct"));
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
-	geno_kernel_t grp[2][2];
+	geno_kernel_t grp[3][2];
 	pick_group_kernels<4>(minb4, grp[0][0], grp[0][1]);
 	pick_group_kernels<8>(minb8, grp[1][0], grp[1][1]);
-	if (warp_only) grp[0][0] = grp[0][1] = grp[1][0] = grp[1][1] = nullptr;
+	grp[2][0] = k_geno8<4, false, 8, EV_WIDE>; grp[2][1] = k_geno8<4, true, 8, EV_WIDE>;
+	if (getenv("VGB_NO_WIDE")) grp[2][0] = grp[2][1] = nullptr;      // tuning: hand-overs go straight to the warp kernel, as before
+	if (warp_only) for (int i = 0; i < 3; i++) grp[i][0] = grp[i][1] = nullptr;
 	c->warp_kernel = (void *)k;
-	for (int i = 0; i < 2; i++) for (int t = 0; t < 2; t++) c->grp_kernel[i][t] = (void *)grp[i][t];
+	for (int i = 0; i < 3; i++) for (int t = 0; t < 2; t++) c->grp_kernel[i][t] = (void *)grp[i][t];
 	int occ = 0;
 	const size_t smem = sizeof(WarpSmem) * GW;
 	VGB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	VGB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, GW * 32, smem));
 	if (occ < 1) occ = 1;
 	c->geno_grid = (uint32_t)(c->sm_count * occ);
-	for (int gi = 0; gi < 2 && !warp_only; gi++) {
-		const size_t sm = grp_smem_bytes(gi ? 8 : 4);   // hit contexts + one row of counters per warp + the warp's parked reads
+	for (int gi = 0; gi < 3 && !warp_only; gi++) {
+		if (!grp[gi][0]) continue;
+		const size_t sm = grp_smem_bytes(gi ? 8 : 4, gi == 2);   // hit contexts + one row of counters per warp + the warp's parked reads
 		for (int t = 0; t < 2; t++) {
 			VGB_CUDA(c, cudaFuncSetAttribute(grp[gi][t], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
 			// VGB_CARVEOUT: preferred shared-memory share of the unified L1 / shared array in percent (tuning knob; default: the driver's choice)
@@ -562,24 +570,35 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 	a.trace = c->d_trace ? c->d_trace + c->trace_n : nullptr;
 	a.spill = (Event *)c->d_spill;
 	a.list = nullptr;
-	a.defer = ck.d_defer;
-	a.klist = nullptr;
+	a.defer = ck.d_defer; a.defer_cnt = 6;
+	a.klist = nullptr; a.in_cnt = 0;
 	a.kdefer = ck.d_defer2;
+	const int tr = a.trace ? 1 : 0;   // per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernels carry none of it
 	const geno_kernel_t warp_kernel = (geno_kernel_t)c->warp_kernel;
-	const geno_kernel_t grp4 = (geno_kernel_t)c->grp_kernel[0][a.trace ? 1 : 0], grp8 = (geno_kernel_t)c->grp_kernel[1][a.trace ? 1 : 0];   // per-read results (VGB_CFG_TRACE: tests) are a separate instantiation, so the production kernels carry none of it
+	const geno_kernel_t grp4 = (geno_kernel_t)c->grp_kernel[0][tr], grp8 = (geno_kernel_t)c->grp_kernel[1][tr], grpw = (geno_kernel_t)c->grp_kernel[2][tr];
 	if (grp8) {
-		// 4 lanes per read (up to 4 k-mers: 128..159 bases), then 8 lanes per read for what it handed over (5..8 k-mers), then
-		// one warp per read for the rest (longer reads, more hit contexts than the group kernels keep in shared memory)
+		// 4 lanes per read (up to 4 k-mers: 128..159 bases), then 8 lanes per read for what it handed over (5..8 k-mers), then 8
+		// lanes per read with the wide context list for the reads of both with too many hit contexts, then one warp per read for
+		// the rest (more than 8 k-mers, more contexts than the wide list holds)
 		if (c->use_quad) {
 			grp4<<<c->grp_grid[0], GW * 32, grp_smem_bytes(4), c->stream>>>(a);
-			a.klist = ck.d_defer2;
+			a.klist = ck.d_defer2; a.in_cnt = 9;
 			c->launches++;
 		}
 		a.kdefer = nullptr;
 		grp8<<<c->grp_grid[1], GW * 32, grp_smem_bytes(8), c->stream>>>(a);
-		a.list = ck.d_defer;
+		c->launches++;
+		if (grpw) {
+			a.klist = ck.d_defer; a.in_cnt = 6;
+			a.defer = ck.d_defer3; a.defer_cnt = 13;
+			grpw<<<c->grp_grid[2], GW * 32, grp_smem_bytes(8, true), c->stream>>>(a);
+			c->launches++;
+			a.list = ck.d_defer3; a.in_cnt = 13;
+		} else {
+			a.list = ck.d_defer; a.in_cnt = 6;
+		}
 		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
-		c->launches += 2;
+		c->launches++;
 	} else {
 		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches++;

@@ -8,10 +8,12 @@
 // All groups of a warp move through the phases together, so every warp-wide shuffle / ballot is executed convergently;
 // loops whose trip count differs per group contain no warp-synchronous operation.
 //
-// Three kernels run per chunk: G = 4 over every read (up to 4 k-mers = up to 159 bases: eight reads and eight probe
-// chains per warp), G = 8 over the reads that one handed over (5..8 k-mers), then k_geno (one warp per read) over what is
-// left: longer reads and reads with more than OCT_EV hit contexts in a pass (a.defer / meta[6]; bit 31 of the list entry
-// = the forward pass is already done and accounted for here).
+// Four kernels run per chunk: G = 4 over every read (up to 4 k-mers = up to 159 bases: eight reads and eight probe
+// chains per warp), G = 8 over the reads that one handed over (5..8 k-mers), G = 8 with EV_WIDE hit contexts per read over the
+// reads either of them gave up on because a pass recorded more than EV_GROUP contexts (reads from repeat families: four
+// reads per warp instead of one, 0.16 -> ~0.05 ms per 2 M GRCh38-shaped reads), then k_geno (one warp per read) over what is
+// left: longer reads and reads with more than EV_WIDE contexts in a pass.  Lists: a.klist / a.in_cnt in, a.defer /
+// a.defer_cnt out; bit 31 of a list entry = the forward pass is already done and accounted for.
 //
 // Rounds: a warp round runs ONE pass (src/qv.cc:778-1510 is "forward pass, then one retry on the reverse complement",
 // :1504-1510) for 32 / G reads.  Reads whose forward pass places nothing are parked in a small per-warp queue (packed
@@ -21,7 +23,8 @@
 #ifndef VGB_OCT_EV
 #define VGB_OCT_EV 24
 #endif
-constexpr int OCT_EV = VGB_OCT_EV;    // hit contexts per read kept in shared memory (16 measured the same on S1 and at GRCh38 size)
+constexpr int EV_GROUP = VGB_OCT_EV;  // hit contexts per read kept in shared memory (16 measured the same on S1 and at GRCh38 size)
+constexpr int EV_WIDE = 64;           // ... in the instantiation behind them (4 k-mers x 10 aux columns + neighbours fit)
 
 // per-round counters of one read, in the group's shared memory (committed when the round ends, unless the read is
 // deferred in this round); the first eight A_* slots of the per-warp accumulator have the same meaning
@@ -34,8 +37,9 @@ struct __align__(8) GEvent {
 	uint32_t X;       // read position this context votes for
 	uint32_t meta;    // bits 0-7 modified base (0xFF none) | 8-15 k-mer index | 16 list (0 ref, 1 snp) | 17 votes
 };
+template <int EVN>
 struct OctSmem {
-	GEvent ev[OCT_EV];
+	GEvent ev[EVN];
 	uint32_t st[8];
 	uint32_t ev_count;
 	uint32_t pad;
@@ -46,10 +50,11 @@ struct Pend {
 	uint32_t r, K, lowq, pad;         // read index in the chunk, k-mer count, quality gates (bit i = k-mer i)
 };
 
-__device__ __forceinline__ void emit8(OctSmem *os, uint64_t kmer, uint32_t pos, uint32_t offset, uint32_t mod, uint32_t kidx, uint32_t list)
+template <int EVN>
+__device__ __forceinline__ void emit8(OctSmem<EVN> *os, uint64_t kmer, uint32_t pos, uint32_t offset, uint32_t mod, uint32_t kidx, uint32_t list)
 {
 	const uint32_t i = atomicAdd(&os->ev_count, 1u);
-	if (i >= OCT_EV) return;                                  // overflow: the read is deferred after this pass
+	if (i >= (uint32_t)EVN) return;                           // overflow: the read is deferred after this pass
 	GEvent e;
 	e.kmer = kmer; e.X = pos - offset; e.meta = mod | (kidx << 8) | (list << 16);
 	os->ev[i] = e;
@@ -61,7 +66,8 @@ __device__ __forceinline__ void emit8(OctSmem *os, uint64_t kmer, uint32_t pos, 
 // a SNP site (:990-991) and a SNP neighbour when the modified base IS the SNP base (:1055).
 // Entries that stand for 2..10 positions go through their aux row; the loop is kept rolled (rare, and this body is
 // instantiated at three call sites: code size is what the instruction cache sees).
-__device__ __forceinline__ void hit8(const DevIndex &ix, OctSmem *os, uint32_t list, uint64_t kmer, uint32_t v, uint32_t fi, uint32_t d,
+template <int EVN>
+__device__ __forceinline__ void hit8(const DevIndex &ix, OctSmem<EVN> *os, uint32_t list, uint64_t kmer, uint32_t v, uint32_t fi, uint32_t d,
                                      uint32_t offset, uint32_t kidx)
 {
 	if (v == POS_AMBIGUOUS) return;
@@ -123,9 +129,10 @@ __device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &off)
 	return ((uint64_t)khi << 32) | klo;
 }
 
-template <int MINB, bool TRACE, int G>
+template <int MINB, bool TRACE, int G, int EVN>
 __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 {
+	typedef OctSmem<EVN> OS;
 	static_assert(G == 4 || G == 8, "lanes per read");
 	constexpr uint32_t R = 32 / G;                // reads per warp round
 	constexpr uint32_t GM = (1u << G) - 1u;
@@ -135,14 +142,14 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 	const uint32_t ol = lane & (G - 1);           // lane inside the group = k-mer index this lane owns
 	const uint32_t ob = lane & ~(uint32_t)(G - 1);   // first lane of the group
 	const uint32_t gi = lane / G;                 // group inside the warp
-	OctSmem *os = reinterpret_cast<OctSmem *>(smem_raw) + (threadIdx.x / G);
+	OS *os = reinterpret_cast<OS *>(smem_raw) + (threadIdx.x / G);
 	// one row of 16 counters per warp, then the warp's queue of parked reads
-	uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * R) + (threadIdx.x >> 5) * 16;
-	Pend<G> *pend = reinterpret_cast<Pend<G> *>(smem_raw + sizeof(OctSmem) * GW * R + GW * 16 * sizeof(uint32_t)) + (threadIdx.x >> 5) * PEND_CAP;
+	uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OS) * GW * R) + (threadIdx.x >> 5) * 16;
+	Pend<G> *pend = reinterpret_cast<Pend<G> *>(smem_raw + sizeof(OS) * GW * R + GW * 16 * sizeof(uint32_t)) + (threadIdx.x >> 5) * PEND_CAP;
 	const DevIndex &ix = a.ix;
-	// list mode (the 8-lane instantiation behind the 4-lane one): only the reads the 4-lane kernel handed over (5..8 k-mers)
-	const uint32_t n_reads = a.klist ? a.meta[9] : a.meta[1];
-	uint32_t *work = a.meta + (a.klist ? 10 : 2);
+	// list mode (the instantiations behind the 4-lane one): only the reads handed over by the kernels in front
+	const uint32_t n_reads = a.klist ? a.meta[a.in_cnt] : a.meta[1];
+	uint32_t *work = a.meta + (a.klist ? a.in_cnt + 1 : 2);
 	const uint32_t *ls0 = a.line_start + a.meta[11];      // first line of the chunk's own records (non-zero only for BGZF windows)
 	const uint32_t FULL = 0xffffffffu;
 #define OSHFL(v, src) __shfl_sync(FULL, (v), ob | (src))
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 
 	for (;;) {
 		uint32_t pass, r = 0, K = 0;
-		bool have = false, run = false, defer = false, wide = false, bad = false, skipped = false, lowq = false;
+		bool have = false, run = false, defer = false, wide = false, bad = false, skipped = false, lowq = false, dretry = false;
 		uint64_t kmer = 0;
 
 		if (npend >= R || (!fresh_left && npend)) {
@@ -181,6 +188,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			pass = 0;
 			have = r0 + gi < n_reads;
 			if (have) r = a.klist ? __ldg(a.klist + r0 + gi) : r0 + gi;
+			dretry = (r >> 31) != 0;                          // list entry: forward pass done where the read came from, retry only
+			r &= 0x7FFFFFFFu;
 
 			// ---- record framing (src/qv.cc:760-779): line starts 4r .. 4r+4 ----
 			uint32_t lsv = 0, lsn = 0;
@@ -208,7 +217,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (bad || skipped) active = false;
 			// quality gate of k-mer i = i-th quality CHARACTER, signed compare (src/qv.cc:836,943; F8)
 			if (active && ol < K) lowq = ((int)(signed char)__ldg(a.text + qual_s + ol) - QUALITY_SCORE) < 0;
-			run = active;
+			run = active && !dretry;
+			dretry = dretry && active;                        // packed and gated here, parked below, run in a retry round
 		}
 
 		os->st[ol] = 0;
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		// two contexts with the same X come from different k-mer positions iff their k-mer indices differ (kmer_pos = X + 32 i)
 		uint32_t E = run ? os->ev_count : 0;
 		if (run && ol == 0) os->st[S_EVENTS] = E;
-		if (E > OCT_EV) { defer = true; E = 0; }              // too many contexts for shared memory: redo this pass in k_geno
+		if (E > (uint32_t)EVN) { defer = true; E = 0; }       // too many contexts for shared memory: redo this pass in the next kernel
 		const bool vrun = run && !defer;
 		for (uint32_t e = ol; e < E; e += G) {
 			GEvent *p = &os->ev[e];
@@ -417,7 +427,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		const bool ambiguous = has_best && xmin != xmax;
 		const bool process = vrun && has_best && !ambiguous;   // freq > 1 is implied by two distinct k-mer positions (:1375)
 		const uint32_t target = xmin;
-		const bool retry = vrun && !process && pass == 0;       // park it: one retry on the reverse complement (:1504-1510)
+		const bool retry = (vrun && !process && pass == 0) || dretry;   // park it: one retry on the reverse complement (:1504-1510)
 
 		// ---- park the reads that go to a retry round (warp-wide compaction over the group leaders) ----
 		const uint32_t lowqm = OBALLOT(lowq);
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (wide && G == 4) {
 				a.kdefer[atomicAdd(&a.meta[9], 1u)] = r;          // 5..8 k-mers: the 8-lane instantiation takes it, from the start
 			} else if (wide || defer) {
-				a.defer[atomicAdd(&a.meta[6], 1u)] = r | (pass << 31);
+				a.defer[atomicAdd(&a.meta[a.defer_cnt], 1u)] = r | (pass << 31);
 			} else {
 				if (run) { atomicAdd(&acc[A_PASSES], 1u); os->st[S_EXACT] = 2u * K; os->st[S_BF] = 2u * os->st[S_LOWQ]; }
 				if (!retry) {
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 	// ---- statistics: one set of atomics per CTA, and only for counters that moved ----
 	__syncthreads();
 	if (threadIdx.x < 14) {
-		uint32_t *all = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OctSmem) * GW * R);
+		uint32_t *all = reinterpret_cast<uint32_t *>(smem_raw + sizeof(OS) * GW * R);
 		unsigned long long v = 0;
 #pragma unroll
 		for (int w = 0; w < GW; w++) v += all[w * 16 + threadIdx.x];

@@ -26,10 +26,11 @@ struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i
 	uint32_t *d_blk_counts = nullptr; // newline count per 4 KiB tile, then its exclusive scan
 	uint32_t *d_defer = nullptr;      // read indices the group kernels hand to the warp-per-read kernel
 	uint32_t *d_defer2 = nullptr;     // read indices the 4-lane kernel hands to the 8-lane kernel
+	uint32_t *d_defer3 = nullptr;     // read indices the wide-list kernel hands to the warp-per-read kernel
 	uint8_t *d_comp = nullptr;        // BGZF: compressed members of the chunk (allocated at the first vgb_submit_bgzf)
 	BgzfBlock *d_blk = nullptr, *h_blk = nullptr;   // their table, device copy and pinned staging
 	uint32_t blk_cap = 0;
-	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter [11] first line of the chunk's own records [12] BGZF member counter
+	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter [11] first line of the chunk's own records [12] BGZF member counter [13] reads for the warp kernel [14] their work counter
 	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, g0 = nullptr;
 	bool busy = false;
 };
@@ -68,9 +69,11 @@ struct vgb_ctx {
 	uint32_t geno_grid = 0;
 	// kernel choice of this context (geno_prepare): instantiation + persistent grid per kernel; nothing process-wide
 	void *warp_kernel = nullptr;
-	void *grp_kernel[2][2] = {};     // [lanes per read: 0 = 4, 1 = 8][trace]
-	uint32_t grp_grid[2] = {};
+	void *grp_kernel[3][2] = {};     // [0: 4 lanes per read, 1: 8 lanes, 2: 8 lanes with the wide context list][trace]
+	uint32_t grp_grid[3] = {};
 	bool use_quad = true;
+	bool inflate_ready = false;       // k_inflate_bgzf: shared-memory attribute set, grid sized
+	uint32_t inflate_grid = 0;
 
 	// host-side statistics
 	uint64_t chunks = 0, chunk_bytes = 0, launches = 0;
