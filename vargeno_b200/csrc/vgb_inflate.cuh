@@ -4,16 +4,20 @@
 // (experiment/experiment.md:20-27).  BGZF (the blocked gzip of bgzip / htslib) is a series of independent gzip members of at
 // most 64 KiB each, so the members of a chunk inflate in parallel on the device and only the compressed bytes cross PCIe.
 //
-// Mapping: lane 0 of the warp walks the Huffman stream (it is inherently serial).  What it produces goes into an 8 KiB ring in
-// the warp's shared memory, never straight to HBM: literals are one shared-memory store, and a match -- every fifth byte of
-// gzip'ed FASTQ starts one, almost all of them 3..12 bytes long and a few hundred bytes back -- is copied ring to ring by lane 0
-// itself.  (The first version wrote literals to global memory and sent every match through an L2 round trip plus a warp
-// broadcast: ~600 cycles per output byte.)  The warp is called in only for what lane 0 cannot do cheaply: flushing the ring
-// to the text buffer with aligned 16-byte stores every 2 KiB, long matches, and matches that reach further back than the ring
-// (read from the text that is already flushed).  The input is read one aligned word per 32 bits, loaded one refill ahead.
-// Decoding tables live beside the ring: a 10-bit direct table for the literal/length alphabet, an 8-bit one for distances, a
-// 7-bit one for the code-length code, canonical count / symbol arrays for the longer codes.  The same source compiles for the
-// host (one "lane"), which is how tests/test_inflate_host.py checks it against zlib without a GPU.
+// Mapping: lane 0 of the warp walks the Huffman stream (it is inherently serial), and the kernel is bound by the instructions
+// that lane issues -- three of four symbols of gzip'ed FASTQ are matches of 3..12 bytes (ncu on the second version: 58 warp
+// instructions per output byte, issue slots 68 % busy), so everything here is about instructions per symbol:
+//   * the bit reader is a POSITION into the stream of aligned 32-bit words: a peek is one funnel shift of the two current words,
+//     a skip is one add plus a test for "crossed into the next word" (the word after next is always loaded ahead);
+//   * a table entry carries code length, number of extra bits and the base value, so code + extra bits come out of ONE peek
+//     (15 + 13 bits at most) and a match costs two table reads, no constant-memory lookups and no refill tests in between;
+//   * what lane 0 produces goes into a ring in the warp's shared memory, never straight to HBM: a literal is one shared-memory
+//     store; a short match is copied by lane 0 itself, ring to ring, or -- when it reaches further back than the ring, which the
+//     3-byte matches of quality strings often do -- from the text that is already flushed.
+// The warp is called in only for flushing the ring to the text buffer with aligned 16-byte stores and for long matches.
+// Decoding tables live beside the ring: a 10-bit direct table for the literal/length alphabet, an 8-bit one for distances (the
+// code-length code borrows it), canonical count / symbol arrays for longer codes.  The same source compiles for the host (one
+// "lane"), which is how tests/test_inflate_host.py checks it against zlib without a GPU.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -21,14 +25,17 @@
 namespace vgb {
 
 constexpr int INF_LIT_BITS = 10, INF_DST_BITS = 8, INF_CL_BITS = 7;
-constexpr uint32_t INF_WIN = 8192;                    // ring size (power of two)
-constexpr uint32_t INF_FLUSH = 2048;                  // lane 0 hands over when this much is waiting in the ring
+constexpr uint32_t INF_WIN = 4096;                    // ring size (power of two)
+constexpr uint32_t INF_FLUSH = 1024;                  // lane 0 hands over when this much is waiting in the ring
 constexpr uint32_t INF_REACH = INF_WIN - 320;         // a match this far back (or less) is still whole in the ring while it is copied
 constexpr uint32_t INF_SOLO = 12;                     // matches up to this length are copied by lane 0 alone
 
+// table entry: bits 0-3 code length (0: not in the direct table), 4-7 extra bits, 8-9 kind, 16-31 literal byte or base value
+enum { INF_K_LIT = 0, INF_K_BASE = 1, INF_K_EOB = 2, INF_K_BAD = 3 };
+
 struct InflateTables {
-	uint16_t lit[1 << INF_LIT_BITS];   // (symbol << 4) | code length, 0 = longer than INF_LIT_BITS: canonical walk
-	uint16_t dst[1 << INF_DST_BITS];   // doubles as the direct table of the code-length code while the lengths are read
+	uint32_t lit[1 << INF_LIT_BITS];
+	uint32_t dst[1 << INF_DST_BITS];   // doubles as the direct table of the code-length code while the lengths are read
 	uint16_t lcount[16], dcount[16];   // codes per length
 	uint16_t lsym[288], dsym[32];      // symbols in canonical order
 	uint16_t code[320];                // canonical code of every symbol (table construction)
@@ -49,7 +56,7 @@ enum { INF_OK = 0, INF_E_INPUT = 1, INF_E_OUTPUT = 2, INF_E_CODE = 3, INF_E_DIST
 #define INF_LANES 32u
 #define INF_SYNC() __syncwarp()
 #define INF_BCAST(v) __shfl_sync(0xffffffffu, (v), 0)
-// bytes another lane of this warp wrote to global memory a moment ago: ordered by the __syncwarp in front, read past L1
+// bytes this warp wrote to global memory a while ago (ordered by a __syncwarp since), read past L1
 #define INF_LOAD_OUT(p) __ldcg(p)
 #define INF_COPY16(d, s) (*reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s))
 #else
@@ -71,59 +78,88 @@ INF_TABLE uint16_t INF_DBASE[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65
 INF_TABLE uint8_t INF_DEXT[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
 INF_TABLE uint8_t INF_ORDER[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
 
-struct InflateBits {                    // LSB-first bit reader over [in, in + n); used by lane 0 only
-	const uint8_t *in;
-	uint32_t n, ip;                     // ip: bytes of the stream that have been moved into bb (a BGZF member is < 64 KiB)
-	uint64_t bb;
-	uint32_t bc;
-	bool over;                          // ran past the end of the input
+// what a symbol of the literal/length (dist = false) or distance alphabet stands for, as a table entry without its code length
+INF_HD uint32_t inf_entry(uint32_t sym, bool dist)
+{
+	if (dist) return sym < 30 ? ((uint32_t)INF_DBASE[sym] << 16) | ((uint32_t)INF_DEXT[sym] << 4) | (INF_K_BASE << 8) : (uint32_t)(INF_K_BAD << 8);
+	if (sym < 256) return (sym << 16) | (INF_K_LIT << 8);
+	if (sym == 256) return (uint32_t)(INF_K_EOB << 8);
+	if (sym < 286) return ((uint32_t)INF_LBASE[sym - 257] << 16) | ((uint32_t)INF_LEXT[sym - 257] << 4) | (INF_K_BASE << 8);
+	return (uint32_t)(INF_K_BAD << 8);
+}
+
+// LSB-first bit reader, used by lane 0 only.  The stream is read as aligned 32-bit words W[k] (on the device: from the aligned
+// address at or below the payload, so bit 0 of the payload is bit 8 * (address & 3) of W[0]); `bp` is the position of the next
+// unread bit, and the three words from W[bp / 32] on are in registers.
+struct InflateBits {
+	const uint8_t *in;                  // the payload
+	uint32_t n;                         // its length in bytes (a BGZF member is < 64 KiB)
+	uint32_t bp0, bp, end;              // position of the payload's first bit, of the next unread bit, of the first bit behind the payload
+	uint32_t w0, w1, w2;                // W[bp / 32], the word behind it, and the one behind that (loaded ahead of its use)
 #ifdef __CUDACC__
-	// the stream is read as aligned words W[k]; 32 stream bits = funnel shift of two neighbours by the (constant) misalignment
-	const uint32_t *wp;                 // address of `wnx`
-	uint32_t wlo, wnx, sh;              // W[k], W[k + 1] (loaded one refill ahead of its use), 8 * (address & 3)
+	const uint32_t *base;               // &W[0]
+	uint32_t wmax;                      // last word index that may be loaded: the payload's last word + 2 (member trailer, in the same buffer)
 #endif
 };
 
-INF_HD void inf_start(InflateBits &b, uint32_t at)          // (re)start reading at byte `at` of the stream
+INF_HD uint32_t inf_word(const InflateBits &b, uint32_t k)
 {
-	b.ip = at; b.bb = 0; b.bc = 0;
 #ifdef __CUDACC__
-	// words in front of / behind the payload belong to the same buffer (member header, trailer, the buffer's 64 spare bytes)
-	const uintptr_t a = reinterpret_cast<uintptr_t>(b.in + at);
-	b.wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-	b.sh = (uint32_t)(a & 3) * 8;
-	b.wlo = b.wp[0];
-	b.wp += 1;
-	b.wnx = b.wp[0];
-#endif
-}
-
-// 32 more bits (callers make sure that at most 32 are left)
-INF_HD void inf_refill(InflateBits &b)
-{
-	uint32_t w = 0;
-#ifdef __CUDACC__
-	w = __funnelshift_r(b.wlo, b.wnx, b.sh);
-	b.wlo = b.wnx;
-	b.wp += 1;
-	b.wnx = b.wp[0];                                        // needed at the next refill: its latency hides behind ~8 symbols
+	return b.base[k < b.wmax ? k : b.wmax];
 #else
-	for (int i = 0; i < 4; i++) if (b.ip + i < b.n) w |= (uint32_t)b.in[b.ip + i] << (8 * i);
+	uint32_t w = 0;
+	for (uint32_t i = 0; i < 4; i++) if ((uint64_t)4 * k + i < b.n) w |= (uint32_t)b.in[4 * k + i] << (8 * i);
+	return w;
 #endif
-	if (b.ip >= b.n + 8) b.over = true;                     // a few bytes behind the end are legal look-ahead, more is not
-	b.ip += 4;
-	b.bb |= (uint64_t)w << b.bc;
-	b.bc += 32;
 }
-INF_HD uint32_t inf_take(InflateBits &b, uint32_t k)        // k <= 32
+INF_HD void inf_seek(InflateBits &b, uint32_t byte)          // continue reading at byte `byte` of the payload
 {
-	if (b.bc < k) inf_refill(b);
-	const uint32_t v = (uint32_t)(b.bb & ((1ull << k) - 1ull));
-	b.bb >>= k; b.bc -= k;
+	b.bp = b.bp0 + 8u * byte;
+	const uint32_t k = b.bp >> 5;
+	b.w0 = inf_word(b, k); b.w1 = inf_word(b, k + 1); b.w2 = inf_word(b, k + 2);
+}
+INF_HD void inf_open(InflateBits &b, const uint8_t *in, uint32_t n)
+{
+	b.in = in; b.n = n;
+#ifdef __CUDACC__
+	const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+	b.base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+	b.bp0 = (uint32_t)(a & 3) * 8;
+	b.wmax = ((b.bp0 + 8u * n + 31u) >> 5) + 1u;
+#else
+	b.bp0 = 0;
+#endif
+	b.end = b.bp0 + 8u * n;
+	inf_seek(b, 0);
+}
+// the next 32 bits (the caller uses as many as the code in front of it is long)
+INF_HD uint32_t inf_peek(const InflateBits &b)
+{
+#ifdef __CUDACC__
+	return __funnelshift_r(b.w0, b.w1, b.bp);              // shifts by bp % 32
+#else
+	const uint32_t s = b.bp & 31u;
+	return s ? (b.w0 >> s) | (b.w1 << (32u - s)) : b.w0;
+#endif
+}
+INF_HD void inf_skip(InflateBits &b, uint32_t k)            // k <= 32: at most one word boundary is crossed
+{
+	const uint32_t nb = b.bp + k;
+	if ((nb ^ b.bp) & 32u) {
+		b.w0 = b.w1; b.w1 = b.w2;
+		b.w2 = inf_word(b, (nb >> 5) + 2u);                // needed two words from here: its latency hides behind the symbols in between
+	}
+	b.bp = nb;
+}
+INF_HD uint32_t inf_take(InflateBits &b, uint32_t k)        // k <= 16
+{
+	const uint32_t v = inf_peek(b) & ((1u << k) - 1u);
+	inf_skip(b, k);
 	return v;
 }
 
-// canonical walk (codes longer than the direct table): one bit at a time, as the format defines it
+// canonical walk (codes longer than the direct table): one bit at a time, as the format defines it.  Out of line, and on a COPY
+// of the reader: taking the address of the caller's own would pin it to local memory for the whole per-symbol loop.
 INF_COLD int inf_slow_cold(InflateBits &b, const uint16_t *count, const uint16_t *sym)
 {
 	int code = 0, first = 0, index = 0;
@@ -135,15 +171,13 @@ INF_COLD int inf_slow_cold(InflateBits &b, const uint16_t *count, const uint16_t
 	}
 	return -1;
 }
-
-// the out-of-line helpers work on a COPY of the reader: taking the address of the caller's own would pin it to local memory,
-// and the per-symbol loop would store and reload its bit buffer around every symbol
-INF_HD int inf_slow(InflateBits &b, const uint16_t *count, const uint16_t *sym)
+// -> table entry of the symbol with code length 0 (its bits are consumed already), INF_K_BAD for a bit pattern that is no code
+INF_HD uint32_t inf_slow(InflateBits &b, const uint16_t *count, const uint16_t *sym, bool dist)
 {
 	InflateBits c = b;
 	const int r = inf_slow_cold(c, count, sym);
 	b = c;
-	return r;
+	return r < 0 ? (uint32_t)(INF_K_BAD << 8) : inf_entry((uint32_t)r, dist);
 }
 
 INF_HD uint32_t inf_rev(uint32_t v, int bits)
@@ -158,7 +192,7 @@ INF_HD uint32_t inf_rev(uint32_t v, int bits)
 }
 
 // lens[0 .. n) -> count[], sym[], code[] (lane 0), then the direct table (all lanes).  Returns false for an over-subscribed set.
-INF_HD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym, uint16_t *code, uint16_t *fast, int fast_bits)
+INF_HD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym, uint16_t *code, uint32_t *fast, int fast_bits, bool dist)
 {
 	const uint32_t lane = INF_LANE();
 	uint32_t ok = 1;
@@ -188,26 +222,12 @@ INF_HD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym
 	for (int i = (int)lane; i < n; i += (int)INF_LANES) {
 		const int l = lens[i];
 		if (l == 0 || l > fast_bits) continue;
+		const uint32_t e = inf_entry((uint32_t)i, dist) | (uint32_t)l;
 		const uint32_t r = inf_rev(code[i], l);
-		for (uint32_t k = r; k < (1u << fast_bits); k += 1u << l) fast[k] = (uint16_t)((i << 4) | l);
+		for (uint32_t k = r; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
 	}
 	INF_SYNC();
 	return true;
-}
-
-INF_HD int inf_decode_lit(InflateBits &b, const InflateTables &t)
-{
-	if (b.bc < 32) inf_refill(b);
-	const uint16_t e = t.lit[b.bb & ((1u << INF_LIT_BITS) - 1)];
-	if (e) { b.bb >>= (e & 15); b.bc -= (e & 15); return e >> 4; }
-	return inf_slow(b, t.lcount, t.lsym);
-}
-INF_HD int inf_decode_dst(InflateBits &b, const InflateTables &t)
-{
-	if (b.bc < 32) inf_refill(b);
-	const uint16_t e = t.dst[b.bb & ((1u << INF_DST_BITS) - 1)];
-	if (e) { b.bb >>= (e & 15); b.bc -= (e & 15); return e >> 4; }
-	return inf_slow(b, t.dcount, t.dsym);
 }
 
 // HLIT / HDIST / HCLEN and the code lengths of a dynamic block (RFC 1951 3.2.7), lane 0 only.  The 19-symbol code-length code
@@ -227,21 +247,21 @@ INF_COLD uint32_t inf_read_lengths_cold(InflateBits &b, InflateTables &t)
 	for (int len = 1; len <= 7; len++) { left <<= 1; left -= cnt[len]; if (left < 0) return 1; }
 	uint32_t c = 0;
 	for (int len = 1; len <= 7; len++) { c = (c + cnt[len - 1]) << 1; next[len] = (uint16_t)c; }
-	uint16_t *fast = t.dst;
+	uint32_t *fast = t.dst;
 	for (int i = 0; i < (1 << INF_CL_BITS); i++) fast[i] = 0;
 	for (int i = 0; i < 19; i++) {
 		const int l = cl[i];
 		if (!l) continue;
 		const uint32_t r = inf_rev(next[l]++, l);
-		for (uint32_t k = r; k < (1u << INF_CL_BITS); k += 1u << l) fast[k] = (uint16_t)((i << 4) | l);
+		for (uint32_t k = r; k < (1u << INF_CL_BITS); k += 1u << l) fast[k] = (uint32_t)((i << 4) | l);
 	}
 	uint32_t idx = 0;
 	while (idx < nlen + ndist) {
-		if (b.bc < 32) inf_refill(b);
-		const uint16_t e = fast[b.bb & ((1u << INF_CL_BITS) - 1)];
+		const uint32_t e = fast[inf_peek(b) & ((1u << INF_CL_BITS) - 1)];
 		if (!e) return 1;                                   // a bit pattern no code of an incomplete set stands for
-		b.bb >>= (e & 15); b.bc -= (e & 15);
+		inf_skip(b, e & 15);
 		const uint32_t sym = e >> 4;
+		if (b.bp > b.end) return 1;
 		if (sym < 16) { t.lens[idx++] = (uint8_t)sym; continue; }
 		uint32_t rep, val = 0;
 		if (sym == 16) { if (idx == 0) return 1; val = t.lens[idx - 1]; rep = 3 + inf_take(b, 2); }
@@ -257,7 +277,6 @@ INF_COLD uint32_t inf_read_lengths_cold(InflateBits &b, InflateTables &t)
 	for (uint32_t i = ndist; i < 30; i++) t.lens[288 + i] = 0;
 	return 0;
 }
-
 INF_HD uint32_t inf_read_lengths(InflateBits &b, InflateTables &t)
 {
 	InflateBits c = b;
@@ -300,29 +319,29 @@ INF_HD int inflate_block(const uint8_t *in, uint64_t in_len, uint8_t *out, uint3
 	uint8_t *ring = ws.ring;
 	const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
 	InflateBits b;
-	b.in = in; b.n = (uint32_t)(in_len < 0xFFFFFF00ull ? in_len : 0xFFFFFF00ull); b.over = false;
-	inf_start(b, 0);
+	inf_open(b, in, (uint32_t)(in_len < 0x10000000ull ? in_len : 0x10000000ull));
 	uint32_t pos = 0, flushed = 0;     // bytes produced / bytes of them that are in the text buffer; the same in every lane
 	int status = INF_OK;
 	for (;;) {
 		// ---- block header (lane 0 reads, everybody learns the type) ----
 		uint32_t hdr = 0;
-		if (lane == 0) hdr = inf_take(b, 3);
+		if (lane == 0) { hdr = inf_take(b, 3); if (b.bp > b.end) hdr |= 8u; }
 		hdr = INF_BCAST(hdr);
+		if (hdr & 8u) { status = INF_E_INPUT; break; }
 		const uint32_t last = hdr & 1u, type = hdr >> 1;
 		if (type == 0) {
 			// stored: skip to the byte boundary, LEN / NLEN, raw bytes (copied by all lanes, straight into the text buffer; the
 			// ring keeps the end of them for the matches of the blocks behind)
 			uint32_t len = 0, src = 0, bad = 0;
 			if (lane == 0) {
-				inf_take(b, b.bc & 7u);
-				len = inf_take(b, 16);
-				const uint32_t nlen = inf_take(b, 16);
-				if ((len ^ 0xFFFFu) != nlen) bad = 1;
-				const uint32_t at = b.ip - (b.bc >> 3);           // whole bytes still in the bit buffer belong to the raw data
-				src = at;
-				if ((uint64_t)at + len > b.n) bad = 1;
-				else inf_start(b, at + len);
+				inf_skip(b, (8u - (b.bp & 7u)) & 7u);
+				const uint32_t w = inf_peek(b);
+				inf_skip(b, 32);
+				len = w & 0xFFFFu;
+				if ((len ^ 0xFFFFu) != (w >> 16)) bad = 1;
+				src = (b.bp - b.bp0) >> 3;
+				if (b.bp > b.end || (uint64_t)src + len > b.n) bad = 1;
+				else inf_seek(b, src + len);
 			}
 			len = INF_BCAST(len); src = INF_BCAST(src); bad = INF_BCAST(bad);
 			if (bad) { status = INF_E_STORED; break; }
@@ -349,65 +368,84 @@ INF_HD int inflate_block(const uint8_t *in, uint64_t in_len, uint8_t *out, uint3
 				bad = INF_BCAST(bad);
 				if (bad) { status = INF_E_CODE; break; }
 			}
-			if (!inf_build(t.lens, 288, t.lcount, t.lsym, t.code, t.lit, INF_LIT_BITS) ||
-			    !inf_build(t.lens + 288, 30, t.dcount, t.dsym, t.code + 288, t.dst, INF_DST_BITS)) { status = INF_E_CODE; break; }
+			if (!inf_build(t.lens, 288, t.lcount, t.lsym, t.code, t.lit, INF_LIT_BITS, false) ||
+			    !inf_build(t.lens + 288, 30, t.dcount, t.dsym, t.code + 288, t.dst, INF_DST_BITS, true)) { status = INF_E_CODE; break; }
 			// ---- symbols: lane 0 decodes into the ring until something needs the warp ----
 			for (;;) {
 				uint32_t ex = 0, mlen = 0, mdist = 0, err = 0;
 				if (lane == 0) {
+					// one test per symbol: room in the ring and in the output
+					const uint32_t lim = flushed + INF_FLUSH < out_cap ? flushed + INF_FLUSH : out_cap;
 					for (;;) {
-						if (pos - flushed >= INF_FLUSH) { ex = EX_FLUSH; break; }
-						// two literals per refill test: 32 bits are enough for a literal of any length and a second one from the
-						// direct table (the pair is what gzip'ed FASTQ mostly consists of)
-						if (b.bc < 32) inf_refill(b);
-						int sym;
-						const uint32_t e = t.lit[b.bb & ((1u << INF_LIT_BITS) - 1)];
-						if (e && e < (256u << 4)) {
-							if (pos >= out_cap) { ex = EX_ERR; err = INF_E_OUTPUT; break; }
-							b.bb >>= (e & 15); b.bc -= (e & 15);
-							ring[(pos + a0) & M] = (uint8_t)(e >> 4);
+						uint32_t win = inf_peek(b);
+						uint32_t e = t.lit[win & ((1u << INF_LIT_BITS) - 1)];
+						if (pos >= lim) {
+							if (pos - flushed >= INF_FLUSH) { ex = EX_FLUSH; break; }
+							// the output is full: only the end-of-block code may follow
+							if ((e & 15u) == 0) e = inf_slow(b, t.lcount, t.lsym, false); else inf_skip(b, e & 15u);
+							if (((e >> 8) & 3u) == INF_K_EOB) ex = EX_EOB;
+							else { ex = EX_ERR; err = ((e >> 8) & 3u) == INF_K_BAD ? INF_E_CODE : INF_E_OUTPUT; }
+							break;
+						}
+						uint32_t cl = e & 15u;
+						if (cl && (e & 0x300u) == (INF_K_LIT << 8)) {        // a literal out of the direct table: the common case
+							ring[(pos + a0) & M] = (uint8_t)(e >> 16);
 							pos++;
-							const uint32_t e2 = t.lit[b.bb & ((1u << INF_LIT_BITS) - 1)];
-							if (e2 && e2 < (256u << 4) && pos < out_cap) {
-								b.bb >>= (e2 & 15); b.bc -= (e2 & 15);
-								ring[(pos + a0) & M] = (uint8_t)(e2 >> 4);
-								pos++;
-							}
+							inf_skip(b, cl);
 							continue;
 						}
-						if (e) { b.bb >>= (e & 15); b.bc -= (e & 15); sym = (int)(e >> 4); }
-						else sym = inf_slow(b, t.lcount, t.lsym);
-						if (sym < 256) {
-							if (sym < 0) { ex = EX_ERR; err = INF_E_CODE; break; }
-							if (pos >= out_cap) { ex = EX_ERR; err = INF_E_OUTPUT; break; }
-							ring[(pos + a0) & M] = (uint8_t)sym;
+						if (cl == 0) { e = inf_slow(b, t.lcount, t.lsym, false); win = inf_peek(b); }
+						const uint32_t kind = (e >> 8) & 3u;
+						if (kind == INF_K_LIT) {
+							ring[(pos + a0) & M] = (uint8_t)(e >> 16);
 							pos++;
 							continue;
 						}
-						if (sym == 256) { ex = EX_EOB; break; }
-						if (sym > 285) { ex = EX_ERR; err = INF_E_CODE; break; }
-						mlen = INF_LBASE[sym - 257] + inf_take(b, INF_LEXT[sym - 257]);
-						const int ds = inf_decode_dst(b, t);
-						if (ds < 0 || ds > 29) { ex = EX_ERR; err = INF_E_CODE; break; }
-						mdist = INF_DBASE[ds] + inf_take(b, INF_DEXT[ds]);
+						if (kind != INF_K_BASE) {
+							if (kind == INF_K_EOB) { inf_skip(b, cl); ex = EX_EOB; } else { ex = EX_ERR; err = INF_E_CODE; }
+							break;
+						}
+						// a match: length = base + extra bits out of the same peek, then the same for the distance
+						uint32_t xb = (e >> 4) & 15u;
+						mlen = (e >> 16) + ((win >> cl) & ((1u << xb) - 1u));
+						inf_skip(b, cl + xb);
+						win = inf_peek(b);
+						e = t.dst[win & ((1u << INF_DST_BITS) - 1)];
+						cl = e & 15u;
+						if (cl == 0) { e = inf_slow(b, t.dcount, t.dsym, true); win = inf_peek(b); }
+						if (((e >> 8) & 3u) != INF_K_BASE) { ex = EX_ERR; err = INF_E_CODE; break; }
+						xb = (e >> 4) & 15u;
+						mdist = (e >> 16) + ((win >> cl) & ((1u << xb) - 1u));
+						inf_skip(b, cl + xb);
 						if (mdist > pos) { ex = EX_ERR; err = INF_E_DIST; break; }
 						if (pos + mlen > out_cap) { ex = EX_ERR; err = INF_E_OUTPUT; break; }
-						if (mlen > INF_SOLO || mdist > INF_REACH) { ex = EX_MATCH; break; }
-						// short match, whole in the ring: byte by byte, four at a time when the pieces cannot overlap
-						uint32_t d = pos + a0, s = pos + a0 - mdist, left = mlen;
-						if (mdist >= 4) {
-							for (; left >= 4; left -= 4, d += 4, s += 4) {
-								const uint8_t v0 = ring[s & M], v1 = ring[(s + 1) & M], v2 = ring[(s + 2) & M], v3 = ring[(s + 3) & M];
+						if (mlen > INF_SOLO) { ex = EX_MATCH; break; }
+						uint32_t d = pos + a0, left = mlen;
+						if (mdist <= INF_REACH) {
+							// whole in the ring: byte by byte, four at a time when the pieces cannot overlap
+							uint32_t s = d - mdist;
+							if (mdist >= 4) {
+								for (; left >= 4; left -= 4, d += 4, s += 4) {
+									const uint8_t v0 = ring[s & M], v1 = ring[(s + 1) & M], v2 = ring[(s + 2) & M], v3 = ring[(s + 3) & M];
+									ring[d & M] = v0; ring[(d + 1) & M] = v1; ring[(d + 2) & M] = v2; ring[(d + 3) & M] = v3;
+								}
+							}
+							for (; left; left--, d++, s++) ring[d & M] = ring[s & M];
+						} else {
+							// further back than the ring reaches: those bytes were flushed to the text long ago (and cannot overlap)
+							const uint8_t *sp = out + (pos - mdist);
+							for (; left >= 4; left -= 4, d += 4, sp += 4) {
+								const uint8_t v0 = INF_LOAD_OUT(sp), v1 = INF_LOAD_OUT(sp + 1), v2 = INF_LOAD_OUT(sp + 2), v3 = INF_LOAD_OUT(sp + 3);
 								ring[d & M] = v0; ring[(d + 1) & M] = v1; ring[(d + 2) & M] = v2; ring[(d + 3) & M] = v3;
 							}
+							for (; left; left--, d++, sp++) ring[d & M] = INF_LOAD_OUT(sp);
 						}
-						for (; left; left--, d++, s++) ring[d & M] = ring[s & M];
 						pos += mlen;
 					}
-					if (b.over) { ex = EX_ERR; err = INF_E_INPUT; }
+					if (b.bp > b.end) { ex = EX_ERR; err = INF_E_INPUT; }      // read past the payload: nothing decoded since is real
 				}
 				INF_SYNC();
-				// what lane 0 found: ex (3 bits) | match length (9 bits) | distance (16 bits), and how far it got
+				// what lane 0 found: ex (3 bits) | error (3 bits) | match length (9 bits) | distance (16 bits), and how far it got
 				uint32_t w0 = ex | (err << 3) | (mlen << 6) | (mdist << 15);
 				w0 = INF_BCAST(w0); pos = INF_BCAST(pos);
 				ex = w0 & 7u; err = (w0 >> 3) & 7u; mlen = (w0 >> 6) & 511u; mdist = w0 >> 15;
@@ -415,7 +453,7 @@ INF_HD int inflate_block(const uint8_t *in, uint64_t in_len, uint8_t *out, uint3
 				if (ex == EX_EOB) break;
 				if (ex == EX_MATCH) {
 					// every byte comes from the part of the output that is already complete (i mod distance): out of the ring, or --
-					// further back than the ring reaches -- out of the text buffer, where those bytes were flushed long ago
+					// further back than the ring reaches -- out of the text buffer
 					if (mdist <= INF_REACH) {
 						for (uint32_t i = lane; i < mlen; i += INF_LANES) {
 							const uint32_t j = mdist >= mlen ? i : i % mdist;
