@@ -413,32 +413,52 @@ INF_HD int inflate_block(const uint8_t *in, uint64_t in_len, uint8_t *out, uint3
 						e = t.dst[win & ((1u << INF_DST_BITS) - 1)];
 						cl = e & 15u;
 						if (cl == 0) { e = inf_slow(b, t.dcount, t.dsym, true); win = inf_peek(b); }
-						if (((e >> 8) & 3u) != INF_K_BASE) { ex = EX_ERR; err = INF_E_CODE; break; }
 						xb = (e >> 4) & 15u;
 						mdist = (e >> 16) + ((win >> cl) & ((1u << xb) - 1u));
 						inf_skip(b, cl + xb);
-						if (mdist > pos) { ex = EX_ERR; err = INF_E_DIST; break; }
-						if (pos + mlen > out_cap) { ex = EX_ERR; err = INF_E_OUTPUT; break; }
-						if (mlen > INF_SOLO) { ex = EX_MATCH; break; }
-						uint32_t d = pos + a0, left = mlen;
+						// one test for everything that takes the match away from this lane: the three ways it can be wrong, and "long"
+						if ((((e >> 8) & 3u) != INF_K_BASE) | (mdist > pos) | (pos + mlen > out_cap) | (mlen > INF_SOLO)) {
+							if (((e >> 8) & 3u) != INF_K_BASE) { ex = EX_ERR; err = INF_E_CODE; }
+							else if (mdist > pos) { ex = EX_ERR; err = INF_E_DIST; }
+							else if (pos + mlen > out_cap) { ex = EX_ERR; err = INF_E_OUTPUT; }
+							else ex = EX_MATCH;
+							break;
+						}
+						// short match, copied here.  Source: the ring, or -- further back than the ring reaches -- the text that was
+						// flushed long ago (those bytes cannot overlap the copy).  Neither piece wraps around the ring's end except
+						// once per 4 KiB: the common case is plain byte moves with constant offsets.
+						const uint32_t d = (pos + a0) & M;
 						if (mdist <= INF_REACH) {
-							// whole in the ring: byte by byte, four at a time when the pieces cannot overlap
-							uint32_t s = d - mdist;
-							if (mdist >= 4) {
-								for (; left >= 4; left -= 4, d += 4, s += 4) {
-									const uint8_t v0 = ring[s & M], v1 = ring[(s + 1) & M], v2 = ring[(s + 2) & M], v3 = ring[(s + 3) & M];
-									ring[d & M] = v0; ring[(d + 1) & M] = v1; ring[(d + 2) & M] = v2; ring[(d + 3) & M] = v3;
+							const uint32_t sr = (pos + a0 - mdist) & M;
+							if (d + mlen <= INF_WIN && sr + mlen <= INF_WIN) {
+								const uint8_t *sp = ring + sr;
+								uint8_t *dp = ring + d;
+								if (mdist >= 4) {
+									uint32_t i = 0;
+									for (; i + 4 <= mlen; i += 4) {
+										const uint8_t v0 = sp[i], v1 = sp[i + 1], v2 = sp[i + 2], v3 = sp[i + 3];
+										dp[i] = v0; dp[i + 1] = v1; dp[i + 2] = v2; dp[i + 3] = v3;
+									}
+									for (; i < mlen; i++) dp[i] = sp[i];
+								} else {
+									for (uint32_t i = 0; i < mlen; i++) dp[i] = sp[i];       // overlapping: strictly in order
 								}
+							} else {
+								for (uint32_t i = 0; i < mlen; i++) ring[(d + i) & M] = ring[(sr + i) & M];
 							}
-							for (; left; left--, d++, s++) ring[d & M] = ring[s & M];
 						} else {
-							// further back than the ring reaches: those bytes were flushed to the text long ago (and cannot overlap)
 							const uint8_t *sp = out + (pos - mdist);
-							for (; left >= 4; left -= 4, d += 4, sp += 4) {
-								const uint8_t v0 = INF_LOAD_OUT(sp), v1 = INF_LOAD_OUT(sp + 1), v2 = INF_LOAD_OUT(sp + 2), v3 = INF_LOAD_OUT(sp + 3);
-								ring[d & M] = v0; ring[(d + 1) & M] = v1; ring[(d + 2) & M] = v2; ring[(d + 3) & M] = v3;
+							if (d + mlen <= INF_WIN) {
+								uint8_t *dp = ring + d;
+								uint32_t i = 0;
+								for (; i + 4 <= mlen; i += 4) {
+									const uint8_t v0 = INF_LOAD_OUT(sp + i), v1 = INF_LOAD_OUT(sp + i + 1), v2 = INF_LOAD_OUT(sp + i + 2), v3 = INF_LOAD_OUT(sp + i + 3);
+									dp[i] = v0; dp[i + 1] = v1; dp[i + 2] = v2; dp[i + 3] = v3;
+								}
+								for (; i < mlen; i++) dp[i] = INF_LOAD_OUT(sp + i);
+							} else {
+								for (uint32_t i = 0; i < mlen; i++) ring[(d + i) & M] = INF_LOAD_OUT(sp + i);
 							}
-							for (; left; left--, d++, sp++) ring[d & M] = INF_LOAD_OUT(sp);
 						}
 						pos += mlen;
 					}
