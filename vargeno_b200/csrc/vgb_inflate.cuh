@@ -50,7 +50,7 @@ enum { INF_OK = 0, INF_E_INPUT = 1, INF_E_OUTPUT = 2, INF_E_CODE = 3, INF_E_DIST
 
 #ifdef __CUDACC__
 #define INF_HD __device__ __forceinline__
-#define INF_COLD __device__ __noinline__
+#define INF_COLD static __device__ __noinline__     // static: nvcc's host pass emits a stub per out-of-line device function; it must not be exported
 #define INF_TABLE static __constant__
 #define INF_LANE() (threadIdx.x & 31u)
 #define INF_LANES 32u
@@ -60,8 +60,8 @@ enum { INF_OK = 0, INF_E_INPUT = 1, INF_E_OUTPUT = 2, INF_E_CODE = 3, INF_E_DIST
 #define INF_LOAD_OUT(p) __ldcg(p)
 #define INF_COPY16(d, s) (*reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s))
 #else
-#define INF_HD inline
-#define INF_COLD inline
+#define INF_HD static inline
+#define INF_COLD static inline
 #define INF_TABLE static const
 #define INF_LANE() 0u
 #define INF_LANES 1u
