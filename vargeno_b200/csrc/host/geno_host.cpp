@@ -860,7 +860,15 @@ int run_geno(const std::string &prefix, const std::string &fastq, const std::str
 				rcs[r] = vgb_ctx_create(&ctxs[r], &cfg);
 				if (rcs[r]) { errs[r] = vgb_last_error(nullptr); return; }
 				rcs[r] = vgb_index_upload(ctxs[r], &ix.view);
-				if (rcs[r]) errs[r] = vgb_last_error(ctxs[r]);
+				if (rcs[r]) { errs[r] = vgb_last_error(ctxs[r]); return; }
+				// the two pinned staging buffers are part of start-up (pinning 2 x chunk_bytes takes a few tenths of a second):
+				// have them before the read loop starts, not inside its first two chunks
+				for (int slot = 0; slot < 2 && !rcs[r]; slot++) {
+					char *buf = nullptr;
+					uint64_t cap = 0;
+					rcs[r] = vgb_pinned_buffer(ctxs[r], slot, &buf, &cap);
+					if (rcs[r]) errs[r] = vgb_last_error(ctxs[r]);
+				}
 			});
 		for (auto &t : th) t.join();
 	}

@@ -67,6 +67,8 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 #define CK(call) do { if ((e = (call)) != cudaSuccess) { set_err(nullptr, VGB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e)); vgb_ctx_destroy(c); return VGB_E_CUDA; } } while (0)
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking));
+
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
 	CK(cudaMalloc((void **)&c->d_stats, sizeof(DevStats)));
 	CK(vgb::memset_sync(c, c->d_stats, 0, sizeof(DevStats)));
@@ -92,6 +94,8 @@ int vgb_ctx_create(vgb_ctx **out, const vgb_config *cfg)
 		CK(cudaEventCreate(&k.t0));
 		CK(cudaEventCreate(&k.t1));
 		CK(cudaEventCreate(&k.g0));
+		CK(cudaEventCreate(&k.g1));
+		CK(cudaEventCreate(&k.h0));
 	}
 #undef CK
 	if (cfg->world_size > 1) {
@@ -125,17 +129,22 @@ void vgb_ctx_destroy(vgb_ctx *c)
 	for (int s = 0; s < 2; s++) {
 		Chunk &k = c->chunk[s];
 		cudaFree(k.d_text); cudaFree(k.d_line_start); cudaFree(k.d_blk_counts); cudaFree(k.d_meta); cudaFree(k.d_defer); cudaFree(k.d_defer2); cudaFree(k.d_defer3);
+		cudaFree(k.d_comp); cudaFree(k.d_blk);
+		if (k.h_blk) cudaFreeHost(k.h_blk);
 		if (k.h_pinned) cudaFreeHost(k.h_pinned);
 		if (k.copied) cudaEventDestroy(k.copied);
 		if (k.done) cudaEventDestroy(k.done);
 		if (k.t0) cudaEventDestroy(k.t0);
 		if (k.t1) cudaEventDestroy(k.t1);
 		if (k.g0) cudaEventDestroy(k.g0);
+		if (k.g1) cudaEventDestroy(k.g1);
+		if (k.h0) cudaEventDestroy(k.h0);
 	}
 	cudaFree(c->d_stats); cudaFree(c->d_tables); cudaFree(c->d_trace);
 	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
 	delete c;
 }
 
@@ -191,13 +200,20 @@ static void collect_times(vgb_ctx *c, int slot)
 	cudaEventSynchronize(k.done);
 	float a = 0, b = 0;
 	if (cudaEventElapsedTime(&a, k.t0, k.t1) == cudaSuccess) c->ms_parse += a;
-	if (cudaEventElapsedTime(&b, k.g0, k.done) == cudaSuccess) c->ms_geno += b;
+	if (k.tail) {
+		// main kernels on the kernel stream + hand-over kernels on the tail stream (which ran under the next chunk's kernels:
+		// both intervals include what the overlap costs them)
+		float t = 0;
+		if (cudaEventElapsedTime(&b, k.g0, k.g1) == cudaSuccess) c->ms_geno += b;
+		if (cudaEventElapsedTime(&t, k.h0, k.done) == cudaSuccess) c->ms_geno += t;
+	} else if (cudaEventElapsedTime(&b, k.g0, k.done) == cudaSuccess) c->ms_geno += b;
 	k.busy = false;
 }
 
 // the text of the chunk is (or will be, in stream order) in k.d_text: record framing, then the per-read kernels
 static int process_text(vgb_ctx *c, Chunk &k, uint64_t nbytes, uint64_t first_read_id, int window, uint64_t ov, int last)
 {
+	k.tail = false;
 	if (!window) VGB_CUDA(c, cudaEventRecord(k.t0, c->stream));      // BGZF chunks: recorded in front of the inflate kernel, which counts as parsing
 	int rc = fastq_index_lines(c, k, nbytes, c->stream, window, ov, last);
 	if (rc == VGB_OK) {
@@ -225,7 +241,7 @@ static int process_text(vgb_ctx *c, Chunk &k, uint64_t nbytes, uint64_t first_re
 			rc = geno_launch(c, k, nbytes, first_read_id);
 		}
 	}
-	cudaEventRecord(k.done, c->stream);
+	cudaEventRecord(k.done, k.tail ? c->tail_stream : c->stream);
 	k.busy = true;
 	c->chunks++;
 	c->chunk_bytes += nbytes;
@@ -332,6 +348,7 @@ int vgb_sync(vgb_ctx *c)
 {
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	collect_times(c, 0);
@@ -362,6 +379,7 @@ int vgb_reset_counts(vgb_ctx *c)
 {
 	if (!c) return VGB_E_ARG;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	VGB_CUDA(c, vgb::memset_sync(c, c->d_stats, 0, sizeof(DevStats)));
@@ -398,6 +416,7 @@ int vgb_allreduce_pileup(vgb_ctx *c)
 	if (!c->have_index) return set_err(c, VGB_E_ARG, "no index");
 	if (c->cfg.world_size == 1) return VGB_OK;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));      // the hand-over kernels of the last chunks update the counters too
 	const int rc = nccl_allreduce_u32(c, c->ix.cnt, 2 * c->ix.n_sites);
 	if (rc) return rc;
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -408,6 +427,7 @@ int vgb_fetch_pileup(vgb_ctx *c, uint32_t *ref_cnt, uint32_t *alt_cnt, uint64_t 
 {
 	if (!c || (n_sites && (!ref_cnt || !alt_cnt))) return VGB_E_ARG;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));      // the hand-over kernels of the last chunks update the counters too
 	return fetch_pileup(c, ref_cnt, alt_cnt, n_sites);
 }
 
@@ -415,6 +435,7 @@ int vgb_call(vgb_ctx *c, uint8_t *gtype, double *conf, uint64_t n_sites)
 {
 	if (!c || (n_sites && (!gtype || !conf))) return VGB_E_ARG;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));      // the hand-over kernels of the last chunks update the counters too
 	return call_sites(c, gtype, conf, n_sites);
 }
 
@@ -431,6 +452,7 @@ int vgb_get_stats(vgb_ctx *c, vgb_stats *out)
 {
 	if (!c || !out) return VGB_E_ARG;
 	cudaSetDevice(c->device);
+	VGB_CUDA(c, cudaStreamSynchronize(c->tail_stream));      // the hand-over kernels of the last chunks update the counters too
 	VGB_CUDA(c, cudaStreamSynchronize(c->stream));
 	collect_times(c, 0);
 	collect_times(c, 1);

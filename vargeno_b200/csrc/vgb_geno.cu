@@ -519,6 +519,8 @@ int geno_prepare(vgb_ctx *c)
 	if (const char *e = getenv("VGB_GENO_MINB")) minb = atoi(e);
 	if (const char *e = getenv("VGB_GENO8_MINB")) minb8 = atoi(e);
 	if (const char *e = getenv("VGB_GENO4_MINB")) minb4 = atoi(e);
+	// VGB_NO_TAIL_OVERLAP: hand-over kernels stay on the kernel stream (measurement switch); per-read results (trace) imply it
+	c->tail_overlap = !(c->cfg.flags & VGB_CFG_TRACE) && !getenv("VGB_NO_TAIL_OVERLAP");
 	const char *kk = getenv("VGB_GENO_KERNEL");
 	const bool warp_only = kk && !strcmp(kk, "warp");
 	c->use_quad = !(kk && !strcmp(kk, "oct"));
@@ -588,18 +590,29 @@ int geno_launch(vgb_ctx *c, Chunk &ck, uint64_t nbytes, uint64_t first_read_id)
 		a.kdefer = nullptr;
 		grp8<<<c->grp_grid[1], GW * 32, grp_smem_bytes(8), c->stream>>>(a);
 		c->launches++;
+		// hand-over kernels: behind the main kernels of this chunk, and (tail_overlap) under the framing and main kernel of the next
+		cudaStream_t ts = c->stream;
+		ck.tail = false;
+		if (c->tail_overlap) {
+			VGB_CUDA(c, cudaEventRecord(ck.g1, c->stream));
+			VGB_CUDA(c, cudaStreamWaitEvent(c->tail_stream, ck.g1, 0));
+			VGB_CUDA(c, cudaEventRecord(ck.h0, c->tail_stream));
+			ts = c->tail_stream;
+			ck.tail = true;
+		}
 		if (grpw) {
 			a.klist = ck.d_defer; a.in_cnt = 6;
 			a.defer = ck.d_defer3; a.defer_cnt = 13;
-			grpw<<<c->grp_grid[2], GW * 32, grp_smem_bytes(8, true), c->stream>>>(a);
+			grpw<<<c->grp_grid[2], GW * 32, grp_smem_bytes(8, true), ts>>>(a);
 			c->launches++;
 			a.list = ck.d_defer3; a.in_cnt = 13;
 		} else {
 			a.list = ck.d_defer; a.in_cnt = 6;
 		}
-		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
+		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, ts>>>(a);
 		c->launches++;
 	} else {
+		ck.tail = false;
 		warp_kernel<<<c->geno_grid, GW * 32, sizeof(WarpSmem) * GW, c->stream>>>(a);
 		c->launches++;
 	}

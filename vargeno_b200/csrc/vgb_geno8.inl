@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			pass = 0;
 			have = r0 + gi < n_reads;
 			if (have) r = a.klist ? __ldg(a.klist + r0 + gi) : r0 + gi;
-			dretry = (r >> 31) != 0;                          // list entry: forward pass done where the read came from, retry only
-			r &= 0x7FFFFFFFu;
+			if (EVN == EV_WIDE) {                             // only this instantiation is handed reads in the middle of their two passes
+				dretry = (r >> 31) != 0;                      // list entry: forward pass done where the read came from, retry only
+				r &= 0x7FFFFFFFu;
+			}
 
 			// ---- record framing (src/qv.cc:760-779): line starts 4r .. 4r+4 ----
 			uint32_t lsv = 0, lsn = 0;
@@ -217,8 +219,11 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 			if (bad || skipped) active = false;
 			// quality gate of k-mer i = i-th quality CHARACTER, signed compare (src/qv.cc:836,943; F8)
 			if (active && ol < K) lowq = ((int)(signed char)__ldg(a.text + qual_s + ol) - QUALITY_SCORE) < 0;
-			run = active && !dretry;
-			dretry = dretry && active;                        // packed and gated here, parked below, run in a retry round
+			run = active;
+			if (EVN == EV_WIDE) {
+				run = active && !dretry;
+				dretry = dretry && active;                    // packed and gated here, parked below, run in a retry round
+			}
 		}
 
 		os->st[ol] = 0;
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		const bool ambiguous = has_best && xmin != xmax;
 		const bool process = vrun && has_best && !ambiguous;   // freq > 1 is implied by two distinct k-mer positions (:1375)
 		const uint32_t target = xmin;
-		const bool retry = (vrun && !process && pass == 0) || dretry;   // park it: one retry on the reverse complement (:1504-1510)
+		const bool retry = (vrun && !process && pass == 0) || (EVN == EV_WIDE && dretry);   // park it: one retry on the reverse complement (:1504-1510)
 
 		// ---- park the reads that go to a retry round (warp-wide compaction over the group leaders) ----
 		const uint32_t lowqm = OBALLOT(lowq);

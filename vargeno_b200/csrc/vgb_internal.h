@@ -32,6 +32,8 @@ struct Chunk {          // one in-flight FASTQ chunk (two slots: copy of chunk i
 	uint32_t blk_cap = 0;
 	uint32_t *d_meta = nullptr;       // [0] n_lines [1] n_reads [2] work counter [3] format error [5] sticky errors [6] deferred reads [7] their work counter [8] framing tile counter [9] reads for the 8-lane kernel [10] their work counter [11] first line of the chunk's own records [12] BGZF member counter [13] reads for the warp kernel [14] their work counter
 	cudaEvent_t copied = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, g0 = nullptr;
+	cudaEvent_t g1 = nullptr, h0 = nullptr;   // end of the main kernels on the kernel stream, start of the hand-over kernels on the tail stream
+	bool tail = false;                        // this chunk's hand-over kernels went to the tail stream (`done` is recorded there)
 	bool busy = false;
 };
 
@@ -42,6 +44,10 @@ struct vgb_ctx {
 	int device = 0;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;   // kernels | H2D copies (chunk i+1 is copied under the kernels of chunk i)
+	// The hand-over kernels of a chunk (wide-list stage, warp-per-read kernel: a few thousand reads from repeat families, a long
+	// dependent chain each, the GPU mostly idle) run here, under the framing and the main kernel of the NEXT chunk.  Not in trace mode.
+	cudaStream_t tail_stream = nullptr;
+	bool tail_overlap = false;
 	std::string err;
 
 	// index (device)
