@@ -25,7 +25,7 @@ HOST_CPP = ["host/vargeno_main.cpp", "host/geno_host.cpp", "host/index_host.cpp"
 HEADERS = ["vgb_common.cuh", "vgb_internal.h", "vgb_geno8.inl", "vgb_inflate.cuh", os.path.join("..", "..", "include", "vgb200.h"), "host/geno_host.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-ccbin", "g++", "--fmad=false"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-ccbin", "g++", "--fmad=false"] + os.environ.get("VGB_NVCC_DEFINES", "").split()   # A/B builds of compile-time variants (tools/sweep_wgs.py, VGB200_LIB)
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-I/usr/local/cuda/include"]
 
 

@@ -177,7 +177,10 @@ int fastq_index_lines(vgb_ctx *c, Chunk &ck, uint64_t nbytes, cudaStream_t st, i
 // ---- BGZF: the gzip members of a chunk inflated on the device, one warp per member (vgb_inflate.cuh) ----
 // 7 warps of 10.6 KiB (ring + tables) per CTA, three CTAs per SM: 21 members in flight per SM.  Members are claimed one at a time
 // through a counter: their cost varies with what they hold.
-constexpr int INF_WARPS = 7;
+#ifndef VGB_INF_WARPS
+#define VGB_INF_WARPS 7
+#endif
+constexpr int INF_WARPS = VGB_INF_WARPS;
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t *comp, const BgzfBlock *blk, uint32_t n_blk, uint8_t *out, uint32_t *meta,
                                                                  uint32_t *next_block)
 {

@@ -24,9 +24,18 @@
 
 namespace vgb {
 
-constexpr int INF_LIT_BITS = 10, INF_DST_BITS = 8, INF_CL_BITS = 7;
-constexpr uint32_t INF_WIN = 4096;                    // ring size (power of two)
-constexpr uint32_t INF_FLUSH = 1024;                  // lane 0 hands over when this much is waiting in the ring
+#ifndef VGB_INF_LIT_BITS
+#define VGB_INF_LIT_BITS 10
+#endif
+#ifndef VGB_INF_DST_BITS
+#define VGB_INF_DST_BITS 8
+#endif
+#ifndef VGB_INF_WIN
+#define VGB_INF_WIN 4096
+#endif
+constexpr int INF_LIT_BITS = VGB_INF_LIT_BITS, INF_DST_BITS = VGB_INF_DST_BITS, INF_CL_BITS = 7;   // the distance table doubles as the 7-bit code-length table
+constexpr uint32_t INF_WIN = VGB_INF_WIN;             // ring size (power of two)
+constexpr uint32_t INF_FLUSH = INF_WIN / 4;           // lane 0 hands over when this much is waiting in the ring
 constexpr uint32_t INF_REACH = INF_WIN - 320;         // a match this far back (or less) is still whole in the ring while it is copied
 constexpr uint32_t INF_SOLO = 12;                     // matches up to this length are copied by lane 0 alone
 
