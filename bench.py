@@ -428,7 +428,13 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if want_cpu:
-            cpu = cpu_port_baseline(wl.host_index, host_sample(g, wl, d_reads, min(B, args.cpu_sample), first, sub_rate, lowq_prob))
+            sample = host_sample(g, wl, d_reads, min(B, args.cpu_sample), first, sub_rate, lowq_prob)
+            cpu, st_o, sites_o = cpu_port_baseline(wl.host_index, sample)
+            cpu["parity"] = parity_against_port(g, sample, st_o, sites_o)
+            if not cpu["parity"]["parity_checked"]:
+                sys.stderr.write("bench.py: PARITY FAILURE against the CPU port on the full-size index: %s\n" % json.dumps(cpu["parity"]))
+                emit({"metric": "reads/s", "value": None, "n_gpus": world, "cpu_baseline": cpu})
+                sys.exit(3)
         elif cpu_skip:
             cpu = {"value": None, "unit": "reads/s", "cores": 0, "kind": "port", "sample": cpu_skip}
         peak, peak_src = measured_peaks()
@@ -511,11 +517,30 @@ def cpu_port_baseline(index, text):
     o.process_fastq(np.ascontiguousarray(text), want_results=False)
     dt = time.perf_counter() - t0
     st = o.stats()
+    sites = o.sites()
     o.close()
     return {"value": st["reads"] / dt, "unit": "reads/s", "cores": 1, "kind": "port",
             "sample": "first %d reads of step 0, oracle/liboracle.so single thread, index resident (image copied back from the GPU once, "
                       "oracle arrays built in %.0f s, outside the timed %.1f s)" % (st["reads"], t_load, dt),
-            "kmer_lookups_per_s": (st["exact_lookups"] + st["nbr_query_lookups"] + st["nbr_scan_reads"]) / dt}
+            "kmer_lookups_per_s": (st["exact_lookups"] + st["nbr_query_lookups"] + st["nbr_scan_reads"]) / dt}, st, sites
+
+
+def parity_against_port(g, text, st_o, sites_o):
+    """The sample the CPU port just processed, through the CUDA path on the full-size index: every per-site counter (saturated
+    like the reference's, src/vartype.h:27) and every lookup / placement counter must be the port's.  The checker's verdict goes
+    into the line; a mismatch ends the run."""
+    g.reset()
+    g.submit_chunk(np.ascontiguousarray(text))         # one call: the sample is smaller than a batch
+    g.sync()
+    r, a = g.pileup()
+    st = g.stats()
+    keys = ("reads", "passes", "placed", "skipped_n", "exact_lookups", "nbr_query_lookups", "nbr_scan_reads", "events", "pileup_incr", "big_kmers")
+    bad = [k for k in keys if k in st_o and int(st[k]) != int(st_o[k])]
+    same = bool(np.array_equal(r, sites_o["ref_cnt"]) and np.array_equal(a, sites_o["alt_cnt"]))
+    return {"parity_checked": same and not bad, "sites_compared": int(sites_o.size), "sites_with_counts": int(np.count_nonzero(r | a)),
+            "reads_compared": int(st["reads"]), "counters_differing": bad,
+            "how": "the CPU port's sample through the CUDA path on the same full-size index: per-site ref/alt counters and the read / pass / "
+                   "placement / lookup / context / increment counters compared"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
