@@ -429,8 +429,14 @@ def run_ours(args):
         cpu = None
         if want_cpu:
             sample = host_sample(g, wl, d_reads, min(B, args.cpu_sample), first, sub_rate, lowq_prob)
-            cpu, st_o, sites_o = cpu_port_baseline(wl.host_index, sample)
+            stress_sample = None
+            if workload == "s2" and not args.skip_shapes:          # the stress shape (every gate open, 2 % substitutions) on the same index
+                stress_sample = host_sample(g, wl, d_reads, min(B, max(1, args.cpu_sample // 4)), first, READ_SETS["s3"][0], READ_SETS["s3"][1])
+            cpu, st_o, sites_o, stress_o = cpu_port_baseline(wl.host_index, sample, stress_sample)
             cpu["parity"] = parity_against_port(g, sample, st_o, sites_o)
+            if stress_o is not None:
+                cpu["parity_s3"] = parity_against_port(g, stress_sample, stress_o[0], stress_o[1])
+                cpu["parity"]["parity_checked"] = cpu["parity"]["parity_checked"] and cpu["parity_s3"]["parity_checked"]
             if not cpu["parity"]["parity_checked"]:
                 sys.stderr.write("bench.py: PARITY FAILURE against the CPU port on the full-size index: %s\n" % json.dumps(cpu["parity"]))
                 emit({"metric": "reads/s", "value": None, "n_gpus": world, "cpu_baseline": cpu})
@@ -507,8 +513,9 @@ def host_sample(g, wl, d_buf, n, first_id, sub_rate, lowq_prob):
     return g.d2h(d_buf, n * rec_bytes())
 
 
-def cpu_port_baseline(index, text):
-    """Bounded single-thread run of the CPU oracle (kind "port") over a prefix of the same reads."""
+def cpu_port_baseline(index, text, stress_text=None):
+    """Bounded single-thread run of the CPU oracle (kind "port") over a prefix of the same reads.  stress_text: a (smaller) sample
+    of the stress read set, run untimed afterwards on the same oracle instance for the parity check of that shape."""
     from oracle import oracle as orc
     t0 = time.perf_counter()
     o = orc.Oracle(index)
@@ -518,11 +525,16 @@ def cpu_port_baseline(index, text):
     dt = time.perf_counter() - t0
     st = o.stats()
     sites = o.sites()
+    stress = None
+    if stress_text is not None:
+        o.reset()
+        o.process_fastq(np.ascontiguousarray(stress_text), want_results=False)
+        stress = (o.stats(), o.sites())
     o.close()
     return {"value": st["reads"] / dt, "unit": "reads/s", "cores": 1, "kind": "port",
             "sample": "first %d reads of step 0, oracle/liboracle.so single thread, index resident (image copied back from the GPU once, "
                       "oracle arrays built in %.0f s, outside the timed %.1f s)" % (st["reads"], t_load, dt),
-            "kmer_lookups_per_s": (st["exact_lookups"] + st["nbr_query_lookups"] + st["nbr_scan_reads"]) / dt}, st, sites
+            "kmer_lookups_per_s": (st["exact_lookups"] + st["nbr_query_lookups"] + st["nbr_scan_reads"]) / dt}, st, sites, stress
 
 
 def parity_against_port(g, text, st_o, sites_o):

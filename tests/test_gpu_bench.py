@@ -33,5 +33,6 @@ def test_bench_line_at_small_scale():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] == 1 and c["value"] > 0
     assert c["parity"]["parity_checked"] is True and c["parity"]["reads_compared"] == 6000 and c["parity"]["counters_differing"] == []
+    assert c["parity_s3"]["parity_checked"] is True and c["parity_s3"]["reads_compared"] == 1500 and c["parity_s3"]["counters_differing"] == []
     assert d["gpu_launches"] > 0
     assert set(d["shapes"]) == {"s3", "s4"} and d["shapes"]["s3"]["value"] > 0
