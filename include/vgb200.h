@@ -107,7 +107,10 @@ typedef struct {
 	uint64_t big_kmers;
 	uint64_t bad_records;        /* records violating the input contract (first error code in vgb_sync) */
 	uint64_t chunks, chunk_bytes;
-	double   gpu_ms_parse, gpu_ms_geno;   /* CUDA-event time of the K1 kernels and of the fused per-read kernel */
+	double   gpu_ms_parse, gpu_ms_geno;   /* CUDA-event time of the K1 kernels (BGZF chunks: the inflate kernel included) and of the per-read
+	                                        * kernels.  The hand-over kernels of a chunk run on a second stream under the next chunk's
+	                                        * kernels, so these are sums of intervals that overlap; with VGB_NO_TAIL_OVERLAP set in the
+	                                        * environment (read at vgb_index_upload) every kernel runs alone and the sums are durations */
 	uint64_t kernel_launches;
 	uint64_t freq_wrap_reads;    /* reads with more than 255 votes for one position: the reference's uint8 counter wraps there
 	                                (src/qv.cc:57-93); never silently used -- vgb_sync fails with VGB_E_OVERFLOW */
