@@ -74,10 +74,14 @@ struct DevIndex {
 	const uint32_t *lo12_ovf;   uint32_t n_lo12_ovf;   // records of 14 words: g, start, 12 absolute ends
 	const SnpEntry *snp;        uint64_t n_snp;
 	const uint32_t *snp_jg;     // 2^24 + 1 entries (src/qv.cc:622-678): the HI24 block the strided scan needs
-	// residue-major copy of the LO40 column for the strided scan (F13): step t of a scan that starts at rank lo examines rank
-	// lo + 11 t, i.e. one residue class mod 11 at consecutive quotients -- stored contiguously here, so the ~23 steps of a
-	// GRCh38-sized block touch ~6 sectors instead of 23:  snp_scan[(r % 11) * snp_scan_stride + r / 11] = LO40(entry r)
-	const uint64_t *snp_scan;   uint64_t snp_scan_stride;
+	// residue-major FILTER column for the strided scan (F13): step t of a scan that starts at rank lo examines rank lo + 11 t,
+	// i.e. one residue class mod 11 at consecutive quotients -- stored contiguously here:
+	//   snp_scan[(r % 11) * snp_scan_stride + r / 11] = low 32 bits of LO40(entry r)
+	// An entry can differ from the query's LO40 in exactly one base only if its low 32 bits are equal to the query's or differ
+	// from them in one base: that test on four bytes per entry sorts out all but ~1e-8 of the entries, and the few that pass are
+	// verified against the full key in `snp`.  The ~23 steps of a GRCh38-sized block touch ~3.5 sectors (an 8-byte LO40 column:
+	// ~6.5, the entries themselves: 23; a 2-byte filter measured worse: more verify reads, one load in flight instead of two).
+	const uint32_t *snp_scan;   uint64_t snp_scan_stride;
 	// secondary view of the SNP dictionary keyed by LO40 (the lower 20 bases), the twin of ref_by_lo: the 36 upper-half
 	// Hamming-1 neighbours of a k-mer (substitutions in bases 20..31, src/qv.cc:1299-1365 with i >= 40) keep its LO40, so
 	// they are exactly the entries of the bucket "same LO40" whose HI24 differs in one base.  One directory request and,
@@ -285,10 +289,27 @@ __device__ __forceinline__ int64_t snp_find_in_block(const DevIndex &ix, uint64_
 	}
 	return -1;
 }
-// LO40 of SNP entry (lo + 11 s): what step s of the reference's strided scan over the block starting at rank lo examines
-__device__ __forceinline__ uint64_t snp_scan_lo40(const DevIndex &ix, uint32_t lo, uint32_t s)
+// one_hamming_distance_32/64 (src/qv.cc:267-312): x != 0 confined to one 2-bit slot -> slot index, else -1
+__device__ __forceinline__ int one_base_slot(uint64_t x)
 {
-	return ldr(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
+	if (x == 0) return -1;
+	const int d = (__ffsll((long long)x) - 1) >> 1;
+	return ((x >> (2 * d)) <= 3ull) ? d : -1;
+}
+// can an entry whose LO40 has these low 32 bits be a Hamming-1 neighbour of a k-mer with low 32 bits klo?  (see snp_scan)
+__device__ __forceinline__ bool scan_candidate(uint32_t klo, uint32_t entry32)
+{
+	const uint32_t x = klo ^ entry32;
+	return x == 0u || one_base_slot((uint64_t)x) >= 0;
+}
+// Step s of the reference's strided scan over the SNP block that starts at rank lo (F13): does the entry it examines, rank
+// lo + 11 s, differ from `kmer` in exactly one of the lower 20 bases?  -> that base and the entry's LO40, or -1
+__device__ __forceinline__ int snp_scan_step(const DevIndex &ix, uint32_t lo, uint32_t s, uint64_t kmer, uint64_t &entry_lo40)
+{
+	const uint32_t e32 = ldr(ix.snp_scan + (uint64_t)(lo % SNP_STRIDE) * ix.snp_scan_stride + lo / SNP_STRIDE + s);
+	if (!scan_candidate((uint32_t)kmer, e32)) return -1;
+	entry_lo40 = ldr(&ix.snp[(uint64_t)lo + (uint64_t)SNP_STRIDE * s].key) & 0xFFFFFFFFFFull;
+	return one_base_slot((kmer & 0xFFFFFFFFFFull) ^ entry_lo40);
 }
 // exact membership through the block of the top 30 bits (entry rank inside the HI24 block is not needed there)
 __device__ __forceinline__ int64_t snp_query(const DevIndex &ix, uint64_t kmer, SnpEntry &out)
@@ -310,13 +331,6 @@ __device__ __forceinline__ bool pile_nonzero(const DevIndex &ix, uint64_t p)
 	return (bits >> (p & 63)) & 1ull;
 }
 
-// one_hamming_distance_32/64 (src/qv.cc:267-312): x != 0 confined to one 2-bit slot -> slot index, else -1
-__device__ __forceinline__ int one_base_slot(uint64_t x)
-{
-	if (x == 0) return -1;
-	const int d = (__ffsll((long long)x) - 1) >> 1;
-	return ((x >> (2 * d)) <= 3ull) ? d : -1;
-}
 #endif
 
 }  // namespace vgb

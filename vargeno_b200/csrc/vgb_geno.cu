@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno(const GenoArgs a)
 							const uint64_t ex = (uint64_t)slo + (uint64_t)SNP_STRIDE * s;
 							st.scan++;
 							if (ex < ix.n_snp) {
-								const uint64_t entry_lo = snp_scan_lo40(ix, slo, s);
-								const int d = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
+								uint64_t entry_lo = 0;
+								const int d = snp_scan_step(ix, slo, s, km, entry_lo);
 								if (d >= 0) {
 									const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ix.snp + slo + s));
 									SnpEntry e;

@@ -331,41 +331,42 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 				}
 				if (hit) hit8(ix, os, list, nb, v, fi, d, offset, i);
 			}
-			// SNP strided scan (F13, :447-462), small mode: step s examines LO40 of rank slo + 11 s = element cbase + s of the
-			// residue-major column.  16 bytes = two steps per load, two loads in flight per lane: a group covers 16 steps per trip
-			// (a GRCh38-sized block has ~23), and the trip holds nothing but loads and compares.  A step that matches is rare: it
-			// leaves the inner loop, records its hit contexts, and the scan resumes behind it.
+			// SNP strided scan (F13, :447-462), small mode: step s examines the entry of rank slo + 11 s = element cbase + s of the
+			// residue-major filter column (the low 32 bits of its LO40: vgb_common.cuh).  16 bytes = four steps per load, two loads in
+			// flight per lane: a group covers 32 steps per trip (a GRCh38-sized block has ~23), and the trip holds nothing but loads
+			// and compares.  An entry that passes the filter is rare: the lane leaves the inner loop, reads the entry's full key from
+			// `snp`, records the hit contexts if it really is a neighbour, and the scan resumes behind it.
 			if (!k_big && k_sB) {
 				// steps whose examined rank slo + 11 s lies past the end of the dictionary match nothing: cut them off
 				const uint32_t n_scan = min(k_sB, (uint32_t)((ix.n_snp - k_slo + (SNP_STRIDE - 1)) / SNP_STRIDE));
 				const uint64_t cbase = (uint64_t)(k_slo % SNP_STRIDE) * ix.snp_scan_stride + k_slo / SNP_STRIDE;
-				const uint32_t mis = (uint32_t)cbase & 1u;    // step 0 is the upper half of its 16-byte pair
+				const uint32_t mis = (uint32_t)cbase & 3u;    // position of step 0 inside its 16-byte quad
 				const uint4 *colp = reinterpret_cast<const uint4 *>(ix.snp_scan + (cbase - mis));
-				const uint32_t npairs = (n_scan + mis + 1u) >> 1;
-				uint32_t sq = ol, sub = 0;                    // next pair of this lane, entry of the trip to resume at
-				while (sq < npairs) {
-					uint32_t found = 4, st_hit = 0, dd_hit = 0;
-					uint64_t lo_hit = 0;
+				const uint32_t nquads = (n_scan + mis + 3u) >> 2;
+				uint32_t sq = ol, sub = 0;                    // next quad of this lane, entry of the trip to resume at
+				while (sq < nquads) {
+					uint32_t found = 8, st_hit = 0;
 					do {
 						const uint4 A = ldr(colp + sq);
 						uint4 B = make_uint4(0, 0, 0, 0);
-						if (sq + G < npairs) B = ldr(colp + sq + G);
+						if (sq + G < nquads) B = ldr(colp + sq + G);
+						const uint32_t w[8] = { A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w };
 #pragma unroll
-						for (uint32_t e = 0; e < 4; e++) {
-							const uint32_t st = 2u * (sq + (e >> 1) * G) + (e & 1u) - mis;   // scan step of this entry (below 0 wraps: fails the range test)
-							const uint4 w = e < 2 ? A : B;
-							const uint64_t entry_lo = (e & 1u) ? (((uint64_t)w.w << 32) | w.z) : (((uint64_t)w.y << 32) | w.x);
-							const int dd = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
-							if (found == 4 && e >= sub && dd >= 0 && st < n_scan) {
-								found = e; st_hit = st; dd_hit = (uint32_t)dd; lo_hit = entry_lo;
-							}
+						for (uint32_t e = 0; e < 8; e++) {
+							const uint32_t st = 4u * (sq + (e >> 2) * G) + (e & 3u) - mis;   // scan step of this entry (below 0 wraps: fails the range test)
+							if (found == 8 && e >= sub && st < n_scan && scan_candidate((uint32_t)km, w[e])) { found = e; st_hit = st; }
 						}
 						sub = found + 1;
-						if (sub >= 4) { sq += 2 * G; sub = 0; }
-					} while (found == 4 && sq < npairs);
-					if (found < 4) {
-						const uint4 raw = ldr(reinterpret_cast<const uint4 *>(ix.snp + k_slo + st_hit));   // REPORTED entry: rank slo + step (F13)
-						hit8(ix, os, 1, (km & 0xFFFFFF0000000000ull) | lo_hit, raw.z, (raw.y >> 8) & 0xFFFFu, dd_hit, offset, i);
+						if (sub >= 8) { sq += 2 * G; sub = 0; }
+					} while (found == 8 && sq < nquads);
+					if (found < 8) {
+						// the filter let this step through: the EXAMINED entry (rank slo + 11 step) decides, the REPORTED one is rank slo + step (F13)
+						const uint64_t entry_lo = ldr(&ix.snp[(uint64_t)k_slo + (uint64_t)SNP_STRIDE * st_hit].key) & 0xFFFFFFFFFFull;
+						const int dd = one_base_slot((km & 0xFFFFFFFFFFull) ^ entry_lo);
+						if (dd >= 0) {
+							const uint4 raw = ldr(reinterpret_cast<const uint4 *>(ix.snp + k_slo + st_hit));
+							hit8(ix, os, 1, (km & 0xFFFFFF0000000000ull) | entry_lo, raw.z, (raw.y >> 8) & 0xFFFFu, (uint32_t)dd, offset, i);
+						}
 					}
 				}
 			}

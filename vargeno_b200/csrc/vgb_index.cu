@@ -378,10 +378,10 @@ __global__ void __launch_bounds__(256) k_xdir_snp(const uint32_t *sjg30, const S
 	x[p] = r;
 }
 
-__global__ void __launch_bounds__(256) k_snp_scan_layout(const SnpEntry *snp, uint64_t n, uint64_t stride, uint64_t *scan)
+__global__ void __launch_bounds__(256) k_snp_scan_layout(const SnpEntry *snp, uint64_t n, uint64_t stride, uint32_t *scan)
 {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r < n) scan[(r % SNP_STRIDE) * stride + r / SNP_STRIDE] = snp[r].key & 0xFFFFFFFFFFull;
+	if (r < n) scan[(r % SNP_STRIDE) * stride + r / SNP_STRIDE] = (uint32_t)snp[r].key;     // low 32 bits of LO40: the scan's filter column
 }
 
 __global__ void __launch_bounds__(256) k_snp_aux(const uint8_t *raw78, uint64_t n, uint32_t *pos_out, uint8_t *info_out)
@@ -632,11 +632,11 @@ int index_upload(vgb_ctx *c, const vgb_index_view *v)
 		ix.snp_by_lo = d_sbl; ix.snp_dir_lo = d_sdl;
 	}
 	{
-		// residue-major LO40 column for the strided scan
+		// residue-major filter column for the strided scan (read four entries per 16-byte load: a little slack behind the last column)
 		const uint64_t stride = (v->n_snp + SNP_STRIDE - 1) / SNP_STRIDE + 1;
-		uint64_t *d_scan = nullptr;
-		if ((rc = dev_alloc(c, &d_scan, stride * SNP_STRIDE))) return rc;
-		VGB_CUDA(c, cudaMemsetAsync(d_scan, 0, stride * SNP_STRIDE * 8, c->stream));
+		uint32_t *d_scan = nullptr;
+		if ((rc = dev_alloc(c, &d_scan, stride * SNP_STRIDE + 16))) return rc;
+		VGB_CUDA(c, cudaMemsetAsync(d_scan, 0, (stride * SNP_STRIDE + 16) * 4, c->stream));
 		if (v->n_snp) k_snp_scan_layout<<<(unsigned)((v->n_snp + 255) / 256), 256, 0, c->stream>>>(d_snp, v->n_snp, stride, d_scan);
 		c->launches++;
 		ix.snp_scan = d_scan; ix.snp_scan_stride = stride;
