@@ -252,14 +252,18 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 		uint32_t qs = 0, qe = 0;
 		if (sb) snp_lo_bucket(ix, kmer & 0xFFFFFFFFFFull, qs, qe);
 		// ---- level 2: exact entries (src/qv.cc:840-937) ----
+		bool rfound = false;
 		if (mine) {
 			uint32_t posx = 0;
 			SnpEntry e;
-			if (rlo < rhi && rmay && ref_find_in_block(ix, (uint32_t)kmer, rlo, rhi, posx) >= 0) hit8(ix, os, 0, kmer, posx, 0, NO_MOD, 32u * ol, ol);
+			if (rlo < rhi && rmay && ref_find_in_block(ix, (uint32_t)kmer, rlo, rhi, posx) >= 0) { rfound = true; hit8(ix, os, 0, kmer, posx, 0, NO_MOD, 32u * ol, ol); }
 			if (f_lo < f_hi && smay && snp_find_in_block(ix, kmer & 0xFFFFFFFFFFull, f_lo, f_hi, e) >= 0)
 				hit8(ix, os, 1, kmer, e.pos, (uint32_t)(e.key >> 40) & 0xFFFFu, NO_MOD, 32u * ol, ol);
 		}
 		if (!rb) { bs = 0; be = 0; }
+		// the k-mer is in the reference dictionary and its LO32 bucket holds one entry: that entry is the k-mer itself, none of
+		// the 48 upper-half neighbours exists -- no need to read the bucket (half of all low-quality k-mers of correct-strand passes)
+		else if (rfound && be - bs == 1u) be = bs;
 		const uint32_t rB = rhi - rlo, sB = shi - slo;
 		const bool big = rB >= BLOCK_SIZE_THRESHOLD;       // src/qv.cc:843,962
 		// lookup accounting: 2K exact queries per pass; per low-quality k-mer the neighbour probes its gates open
