@@ -137,6 +137,14 @@ def test_s3_style_reads_match_the_oracle(shaped):
     assert ost["reads"] == 24_000 and ost["lowq_kmers"] >= 4 * 24_000   # every k-mer of every pass is neighbour-searched
 
 
+@pytest.mark.parametrize("shortscan", ["0", "1"])
+def test_both_scan_instantiations_match_the_oracle(shaped, shortscan, monkeypatch):
+    """The strided-scan instantiation is chosen per index by the mean HI24 block length (VGB_SHORTSCAN overrides): a scaled-down
+    index always gets the short one, the GRCh38-sized one of the benchmark the other -- both must give the oracle's answers."""
+    monkeypatch.setenv("VGB_SHORTSCAN", shortscan)
+    _check(shaped.index, shaped.text3)
+
+
 def test_targeted_reads_fire_big_mode_aux_rows_and_ambiguity(shaped):
     ost, want = _check(shaped.index, shaped.text_t)
     assert ost["big_kmers"] > 100                                       # src/qv.cc:962: ref block >= 100

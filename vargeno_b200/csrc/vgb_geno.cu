@@ -502,8 +502,9 @@ static size_t grp_smem_bytes(int G, bool wide = false)
 }
 
 template <int G>
-static void pick_group_kernels(int minb, geno_kernel_t &k, geno_kernel_t &kt)
+static void pick_group_kernels(int minb, bool shortscan, geno_kernel_t &k, geno_kernel_t &kt)
 {
+	if (minb == 4 && shortscan) { k = k_geno8<4, false, G, EV_GROUP, true>; kt = k_geno8<4, true, G, EV_GROUP, true>; return; }
 	if (minb >= 6) { k = k_geno8<6, false, G, EV_GROUP>; kt = k_geno8<6, true, G, EV_GROUP>; }
 	else if (minb == 5) { k = k_geno8<5, false, G, EV_GROUP>; kt = k_geno8<5, true, G, EV_GROUP>; }
 	else if (minb == 3) { k = k_geno8<3, false, G, EV_GROUP>; kt = k_geno8<3, true, G, EV_GROUP>; }
@@ -526,8 +527,12 @@ int geno_prepare(vgb_ctx *c)
 	c->use_quad = !(kk && !strcmp(kk, "oct"));
 	geno_kernel_t k = minb >= 8 ? k_geno<8> : (minb >= 6 ? k_geno<6> : (minb == 5 ? k_geno<5> : k_geno<4>));
 	geno_kernel_t grp[3][2];
-	pick_group_kernels<4>(minb4, grp[0][0], grp[0][1]);
-	pick_group_kernels<8>(minb8, grp[1][0], grp[1][1]);
+	// mean HI24 block length of the SNP dictionary decides the scan instantiation (see k_geno8): below four entries a scan ends
+	// inside its first load; VGB_SHORTSCAN=0/1 overrides (measurement switch)
+	bool shortscan = (c->ix.n_snp >> 24) < 4;
+	if (const char *e = getenv("VGB_SHORTSCAN")) shortscan = atoi(e) != 0;
+	pick_group_kernels<4>(minb4, shortscan, grp[0][0], grp[0][1]);
+	pick_group_kernels<8>(minb8, shortscan, grp[1][0], grp[1][1]);
 	grp[2][0] = k_geno8<4, false, 8, EV_WIDE>; grp[2][1] = k_geno8<4, true, 8, EV_WIDE>;
 	if (getenv("VGB_NO_WIDE")) grp[2][0] = grp[2][1] = nullptr;      // tuning: hand-overs go straight to the warp kernel, as before
 	if (warp_only) for (int i = 0; i < 3; i++) grp[i][0] = grp[i][1] = nullptr;

@@ -129,7 +129,11 @@ __device__ __forceinline__ uint64_t pack32(const char *p, uint32_t &off)
 	return ((uint64_t)khi << 32) | klo;
 }
 
-template <int MINB, bool TRACE, int G, int EVN>
+// SHORTSCAN: instantiation for SNP dictionaries whose HI24 blocks hold a few entries (a chr22-sized list: two), where the strided
+// scan ends inside its first 16-byte load: the compares of the second load are then skipped by a branch.  With GRCh38-sized
+// blocks (~23 entries) the branch costs more than it saves (-3 % / -5 % of the gain on S2 / S3), without it the short scans pay
+// for eight compares they do not need (+3 % on S1): chosen per index at upload (geno_prepare).
+template <int MINB, bool TRACE, int G, int EVN, bool SHORTSCAN = false>
 __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 {
 	typedef OctSmem<EVN> OS;
@@ -353,10 +357,12 @@ __global__ void __launch_bounds__(GW * 32, MINB) k_geno8(const GenoArgs a)
 					do {
 						const uint4 A = ldr(colp + sq);
 						uint4 B = make_uint4(0, 0, 0, 0);
-						if (sq + G < nquads) B = ldr(colp + sq + G);
+						const bool hasB = sq + G < nquads;
+						if (hasB) B = ldr(colp + sq + G);
 						const uint32_t w[8] = { A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w };
 #pragma unroll
 						for (uint32_t e = 0; e < 8; e++) {
+							if (SHORTSCAN && e == 4 && !hasB) break;
 							const uint32_t st = 4u * (sq + (e >> 2) * G) + (e & 3u) - mis;   // scan step of this entry (below 0 wraps: fails the range test)
 							if (found == 8 && e >= sub && st < n_scan && scan_candidate((uint32_t)km, w[e])) { found = e; st_hit = st; }
 						}
