@@ -696,7 +696,11 @@ def run_reference(args):
             shutil.rmtree(d, ignore_errors=True)
 
     def plan_nproc():
-        n = int((mem_available_gb() - files_gb - 8) // per_proc_gb)
+        avail = mem_available_gb()
+        # one process per core that fits beside the index files (page cache / tmpfs), 8 GB for this process and its read set, and
+        # a margin of 5 % of the box (at least 10 GB): the per-process figure is an estimate, and a box driven out of memory is
+        # worse than one process fewer
+        n = int((avail - files_gb - 8 - max(10.0, 0.05 * avail)) // per_proc_gb)
         n = max(1, min(os.cpu_count() or 1, n))
         return args.ref_procs or n
 
